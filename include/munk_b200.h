@@ -1,0 +1,122 @@
+/*
+ * munk_b200 - C ABI of the B200 (sm_100a) implementation of MUNK's dense FP64 hot path.
+ *
+ * The reference (lrgr/munk) is pure Python and has no FFI layer; its boundary for this path is
+ * the `munk` package API (munk/munk/__init__.py:1-11).  Each entry point below names the
+ * reference call it replaces.  A binding (ctypes, cffi, cgo ...) needs nothing but this header:
+ * plain pointers and sizes, no C++/torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - matrices are row-major FP64 with a leading dimension `ld` in elements; ld must be even
+ *     and base pointers 16-byte aligned (TMA requirement);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls only enqueue
+ *     work unless stated otherwise;
+ *   - return value: 0 = ok, <0 = bad argument, >=1000 CUDA error (1000 + cudaError_t),
+ *     >=2000 matrix not positive definite, >=3000 tensor-map creation failed.
+ *     munk_last_error_string() describes the last failure of the calling thread.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef MUNK_B200_H
+#define MUNK_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct munk_workspace munk_workspace_t; /* per-stream scratch + statistics */
+
+/* Operand storage for munk_dgemm: the contraction index k contiguous, or the free index. */
+#define MUNK_OP_KC 0 /* X[i*ld + k] */
+#define MUNK_OP_MC 1 /* X[k*ld + i] */
+
+/* Structure flags for munk_dgemm (tile granularity 128; see munk_b200/csrc/dgemm.cuh). */
+#define MUNK_GF_TILE_LOWER 1
+#define MUNK_GF_KLO_M 2
+#define MUNK_GF_KLO_N 4
+#define MUNK_GF_KHI_M 8
+#define MUNK_GF_KHI_N 16
+#define MUNK_GF_SYM_MIRROR 32
+
+const char* munk_last_error_string(void);
+int munk_version(void);
+
+/* Workspace: one per (device, stream) in use.  Not thread-safe; re-entrant across workspaces. */
+int munk_workspace_create(int device, munk_workspace_t** ws);
+int munk_workspace_destroy(munk_workspace_t* ws);
+/* kernels enqueued and useful flops enqueued through `ws` since the last reset */
+int munk_workspace_stats(munk_workspace_t* ws, long* launches, double* flops, int reset);
+
+/* Bytes of leaf-inverse storage (`linv`) munk_potrf/munk_trtri need for order n. */
+size_t munk_linv_bytes(int n);
+
+/*
+ * A = I + lam * L(G), dense n x ld, from the undirected edge list (u[e], v[e]), e < nnz, each
+ * edge once, no self loops, indices in sorted-node order.
+ * Replaces: munk/munk/munk.py:82-83 (nx.laplacian_matrix(...).todense(); np.eye + lam*L).
+ * Bit-exact with numpy (diagonal fl(1 + fl(lam*deg)), off-diagonal -lam).
+ */
+int munk_assemble_reglap(munk_workspace_t* ws, int n, int nnz, const int* u, const int* v,
+                         double lam, double* A, long ld, void* stream);
+
+/*
+ * In-place lower Cholesky A = L L^T (row-major; lower triangle read and written; the 128x128
+ * diagonal blocks get zeros above the diagonal, other upper blocks are left untouched).
+ * First half of the replacement for np.linalg.inv at munk/munk/munk.py:83.
+ */
+int munk_potrf(munk_workspace_t* ws, int n, double* A, long ld, double* linv, void* stream);
+
+/* Synchronises `stream`; *info_host = 0 if every pivot so far was positive, else 1 + index of
+ * the first bad column; the device flag is cleared. */
+int munk_potrf_info(munk_workspace_t* ws, int* info_host, void* stream);
+
+/*
+ * In-place W = L^-1 of the factor left by munk_potrf (same linv).  C = W^T is an RKHS factor of
+ * D = A^-1 (C C^T = D); replaces scipy.linalg.eigh + v.dot(diag(sqrt(e))) at
+ * munk/munk/munk.py:87-88 (the factor differs from the reference's by an orthogonal matrix on
+ * the right, which leaves D and the scores C * C2hat^T unchanged).
+ */
+int munk_trtri(munk_workspace_t* ws, int n, double* L, long ld, double* linv, void* stream);
+
+/* D = W^T W, full symmetric n x n (the value np.linalg.inv returns at munk/munk/munk.py:83). */
+int munk_gram_lower(munk_workspace_t* ws, int n, const double* W, long ldw, double* D, long ldd,
+                    void* stream);
+
+/*
+ * C(M x N) = alpha * A(M x K) * B(N x K)^T + beta * C, DMMA tensor cores, TMA-staged operands.
+ * Replaces np.dot / @ at scripts/compute_embeddings.py:81,
+ * experiments/homology-scores-permutation-test/permtest.py:55 and the products inside
+ * munk/munk/munk.py:109-110.
+ */
+int munk_dgemm(munk_workspace_t* ws, int a_layout, int b_layout, int M, int N, int K, double alpha,
+               const double* A, long lda, const double* B, long ldb, double beta, double* C,
+               long ldc, int flags, void* stream);
+
+/* Q[i][l] = W[i][idx[l]] for i >= idx[l], else 0 (n x ldq, columns l >= k are zeroed):
+ * the rows C[idx,:] of C = W^T, transposed (munk/munk/munk.py:109 source_C[source_idxs,:]). */
+int munk_gather_cols_lower(int n, const double* W, long ldw, int k, const int* idx, double* Q,
+                           long ldq, void* stream);
+
+/* C[i][j] = W[j][i] for j >= i, else 0: materialises the upper-triangular factor C = W^T. */
+int munk_transpose_lower(int n, const double* W, long ldw, double* C, long ldc, void* stream);
+
+/* out[g][:] = mean of in[members[gptr[g] .. gptr[g+1])][:]; used to fold duplicated source
+ * landmarks (np.linalg.pinv's minimum-norm least-squares answer, munk/munk/munk.py:109). */
+int munk_group_mean_rows(int ngroups, const int* gptr, const int* members, int ncols,
+                         const double* in, long ldi, double* out, long ldo, void* stream);
+
+/* out[l] = S[r[l]][c[l]] (munk/munk/munk.py:42 scores[source_landmark_idxs, target_landmark_idxs]) */
+int munk_gather_pairs(int npairs, const int* r, const int* c, const double* S, long lds,
+                      double* out, void* stream);
+
+/* Micro-benchmarks used by bench.py / tools to measure the FP64 ceilings of the box.
+ * Each runs on `device`, blocks, and returns TFLOP/s in *tflops. */
+int munk_microbench_dmma(int device, int iters, double* tflops);
+int munk_microbench_dfma(int device, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUNK_B200_H */

@@ -1,0 +1,21 @@
+// Internal interface of the single-GPU factorisations (factor.cu).
+#pragma once
+#include "common.cuh"
+
+namespace munk {
+
+struct Workspace;
+
+// bytes of leaf-inverse storage a matrix of order n needs (one 128x128 block per 128 columns)
+size_t linv_bytes_for(int n);
+
+// In-place lower Cholesky of the row-major SPD matrix A (only the lower triangle is read).
+// On return the lower triangle holds L, the 128x128 diagonal blocks have zeros above the
+// diagonal, `linv` holds the inverses of the diagonal blocks; ws->info is non-zero if a
+// pivot was not positive.  Blocks above the diagonal keep whatever they held.
+int potrf_lower(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t stream);
+
+// In-place inverse of the lower-triangular factor produced by potrf_lower (same linv).
+int trtri_lower(Workspace* ws, int n, double* L, long ld, double* linv, cudaStream_t stream);
+
+}  // namespace munk
