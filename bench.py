@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the MUNK hot path on B200 (driver contract: one JSON line on stdout).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3] [--impl reference]
+
+One "step" = the whole dense pipeline for one synthetic scale-free graph pair of the named
+configuration: Laplacian assembly, Cholesky + triangular inverse of
+source and target (C1 = W1^T, D2 = W2^T W2), landmark projection C2hat, and the n1 x n2 score
+product S = C1 C2hat^T.  At N=1 the workload is BASELINE.json's 20k -> 16k configuration (C3).
+
+  value  = useful FP64 flops of the step (formulae of SURVEY 8d, triangular products counted once)
+           x graph pairs processed by all ranks / device time (CUDA events, max over ranks), inputs
+           already resident in HBM.
+  e2e    = the same through the host-buffer API: edge/index arrays copied H2D every step and
+           C1, C2hat and S copied back into pinned host memory inside the timed region.
+  roofline     = the dominant kernel (the DMMA score GEMM launch) against the measured FP64 DMMA peak.
+  cpu_baseline = the CPU oracle (numpy/scipy port of the reference algorithm) on a bounded sample.
+
+`--impl reference` times the reference's CPU algorithm (oracle port: inv + eigh + pinv + dot via
+numpy/scipy with every host thread) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MUNK pipeline FP64 TFLOP/s (useful flops / end-to-end s), 20k->16k nodes"
+UNIT = "TFLOP/s"
+
+
+def pipeline_flops(n1, n2, k):
+    """Useful flops of the build's algorithm: chol n^3/3 + trtri n^3/3 per graph,
+    D2[Lt,:] rows k*n2^2, Gram k^2*n1 (symmetric... counted dense 2*k^2*n1), projection
+    2*n1*n2*k, triangular score product n1^2*n2."""
+    src = 2.0 * n1 ** 3 / 3.0
+    tgt = 2.0 * n2 ** 3 / 3.0
+    rows = 1.0 * k * n2 ** 2
+    gram = 2.0 * k * k * n1
+    solve = 2.0 * k * k * n2 + 2.0 * k ** 3 / 3.0
+    proj = 2.0 * n1 * n2 * k
+    score = 1.0 * n1 * n1 * n2
+    return dict(source=src, target=tgt, rows=rows, gram=gram, solve=solve, proj=proj, score=score,
+                total=src + tgt + rows + gram + solve + proj + score)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self._stop = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, flag in zip(names, r[3:7]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(cfg_name, rank, n1=None, n2=None):
+    from munk_b200 import pipeline, synthetic
+    c = synthetic.CONFIGS[cfg_name]
+    n1, n2 = n1 or c[0], n2 or c[1]
+    m, H, k = c[2], c[3], c[4]
+    G1, G2, homs = synthetic.make_case(n1, n2, m, min(H, n1, n2), seeds=(1 + 2 * rank, 2 + 2 * rank))
+    inp = pipeline.graph_inputs(G1, G2, homs, min(k, len(homs)))
+    return n1, n2, len(inp["landmark_idxs"]), inp, (G1, G2, homs)
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_pipeline(G1, G2, homs, k):
+    """The reference algorithm (oracle port): embed_networks + np.dot."""
+    from oracle import munk_oracle as oracle
+    t0 = time.time()
+    out = oracle.embed_networks(G1, G2, homs, k)
+    S = oracle.scores(out["C1"], out["C2"])
+    return time.time() - t0, S
+
+
+def cpu_info():
+    import numpy, scipy
+    info = {"cores": os.cpu_count(), "numpy": numpy.__version__, "scipy": scipy.__version__}
+    try:
+        from threadpoolctl import threadpool_info
+        pools = threadpool_info()
+        info["blas"] = ["%s %s x%d" % (p.get("internal_api"), p.get("version"), p.get("num_threads")) for p in pools]
+        info["threads"] = max([p.get("num_threads", 1) for p in pools] + [1])
+    except Exception:
+        info["threads"] = os.cpu_count()
+    return info
+
+
+def cpu_sample(cfg_name, n1, n2, reps=1):
+    """Times the CPU port on an (n1, n2) sample of the workload; returns (TFLOP/s, description)."""
+    _, _, k, _, (G1, G2, homs) = make_inputs(cfg_name, 0, n1, n2)
+    best = min(cpu_pipeline(G1, G2, homs, k)[0] for _ in range(reps))
+    fl = pipeline_flops(n1, n2, k)["total"]
+    return fl / best / 1e12, best, "oracle port (inv+eigh+pinv+dot) on %s-shaped sample n1=%d n2=%d k=%d: %.2f s" % (
+        cfg_name, n1, n2, k, best)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    info = cpu_info()
+    n1, n2 = args.cpu_n1, args.cpu_n2
+    _, _, k, _, (G1, G2, homs) = make_inputs(args.config, 0, n1, n2)
+    for _ in range(min(args.warmup, 1)):
+        cpu_pipeline(G1, G2, homs, k)
+    times = [cpu_pipeline(G1, G2, homs, k)[0] for _ in range(max(1, min(args.steps, args.cpu_max_steps)))]
+    t = sum(times) / len(times)
+    fl = pipeline_flops(n1, n2, k)["total"]
+    val = fl / t / 1e12
+    sample = "oracle port of the reference algorithm on %s-shaped sample n1=%d n2=%d k=%d, %d timed steps" % (
+        args.config, n1, n2, k, len(times))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s sample %d/%d nodes, k=%d (Barabasi-Albert, seeds 1/2)" % (args.config, n1, n2, k),
+                   "note": "useful flops counted with the build's formulae so GPU/CPU ratios are time ratios"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": info.get("threads"), "kind": "port",
+                         "sample": sample, "host": info},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from munk_b200 import pipeline
+    from munk_b200.device import Device, landmark_groups
+    from munk_b200._lib import lib
+    import ctypes
+
+    dev = Device(local)
+    n1, n2, k, inp, graphs = make_inputs(args.config, rank)
+    fl = pipeline_flops(n1, n2, k)
+    tdev = dev.torch_device
+
+    # device-resident inputs for the `value` region
+    e1 = (dev.ints(inp["edges1"][0]), dev.ints(inp["edges1"][1]))
+    e2 = (dev.ints(inp["edges2"][0]), dev.ints(inp["edges2"][1]))
+    s_idx = [a for a, _ in inp["landmark_idxs"]]
+    t_idx = [b for _, b in inp["landmark_idxs"]]
+    uniq, gptr, members = landmark_groups(s_idx)
+    uniq_d, tidx_d = dev.ints(uniq), dev.ints(t_idx)
+
+    # persistent buffers (sized for 180 GB HBM: ~14 GB at C3)
+    A1, A2 = dev.empty(n1, n1), dev.empty(n2, n2)
+    linv1, linv2 = dev.new_linv(n1), dev.new_linv(n2)
+    S_buf = dev.empty(n1, n2)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    phase_ms = {}
+
+    def step(edges1, edges2, uniq_idx, tgt_idx, record=False):
+        marks = []
+
+        def mark(name):
+            if record:
+                e = ev(); e.record(); marks.append((name, e))
+        mark("start")
+        dev.assemble(n1, edges1[0], edges1[1], 0.05, out=A1); mark("assemble_src")
+        dev.potrf(A1, n1, linv=linv1, check_info=False); mark("potrf_src")
+        dev.trtri(A1, n1, linv1); mark("trtri_src")
+        dev.assemble(n2, edges2[0], edges2[1], 0.05, out=A2); mark("assemble_tgt")
+        dev.potrf(A2, n2, linv=linv2, check_info=False); mark("potrf_tgt")
+        dev.trtri(A2, n2, linv2); mark("trtri_tgt")
+        Q1 = dev.gather_cols_lower(A1, n1, uniq_idx)
+        B = dev.target_landmark_rows(A2, n2, tgt_idx)
+        P = dev.project(Q1, n1, B, n2, (gptr, members)); mark("embed")
+        dev.score(A1, n1, P, n2, out=S_buf); mark("score")
+        if record:
+            torch.cuda.current_stream().synchronize()
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                phase_ms.setdefault(name, []).append(a.elapsed_time(b))
+        return P
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 3)):
+        step(e1, e2, uniq_d, tidx_d)
+    barrier()
+    assert dev.potrf_info() == 0
+
+    # ---- timed: value (inputs resident)
+    sampler = ClockSampler(local); sampler.start()
+    dev.stats(reset=True)
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        step(e1, e2, uniq_d, tidx_d, record=True)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    launches, counted_flops = dev.stats(reset=True)
+    clocks = sampler.stop()
+    assert dev.potrf_info() == 0
+
+    # ---- timed: e2e (host buffers in, pinned host results out, every step)
+    h_e1 = [torch.from_numpy(x).pin_memory() for x in inp["edges1"]]
+    h_e2 = [torch.from_numpy(x).pin_memory() for x in inp["edges2"]]
+    import numpy as np
+    h_u = torch.from_numpy(np.asarray(uniq, dtype=np.int32)).pin_memory()
+    h_t = torch.from_numpy(np.asarray(t_idx, dtype=np.int32)).pin_memory()
+    out_C1 = torch.empty((n1, n1), dtype=torch.float64, pin_memory=True)
+    out_P = torch.empty((n1, n2), dtype=torch.float64, pin_memory=True)
+    out_S = torch.empty((n1, n2), dtype=torch.float64, pin_memory=True)
+    h2d = sum(t.numel() * t.element_size() for t in h_e1 + h_e2 + [h_u, h_t])
+    d2h = sum(t.numel() * t.element_size() for t in (out_C1, out_P, out_S))
+
+    def e2e_step():
+        d_e1 = [t.to(tdev, non_blocking=True) for t in h_e1]
+        d_e2 = [t.to(tdev, non_blocking=True) for t in h_e2]
+        P = step(d_e1, d_e2, h_u.to(tdev, non_blocking=True), h_t.to(tdev, non_blocking=True))
+        C1 = dev.transpose_lower(A1, n1)
+        out_C1.copy_(C1[:, :n1], non_blocking=True)
+        out_P.copy_(P[:, :n2], non_blocking=True)
+        out_S.copy_(S_buf[:, :n2], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    w0 = time.perf_counter()
+    q0, q1 = ev(), ev()
+    q0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    q1.record()
+    barrier()
+    e2e_ms = max(q0.elapsed_time(q1), (time.perf_counter() - w0) * 1e3 * 0.0)
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        value = fl["total"] * world / (ms_step * 1e-3) / 1e12
+        e2e_val = fl["total"] * world / (e2e_ms / e2e_steps * 1e-3) / 1e12
+        # FP64 ceilings measured on this box, in this run
+        v = ctypes.c_double()
+        lib.munk_microbench_dmma(local, 20000, ctypes.byref(v)); dmma_peak = v.value
+        a = torch.randn(8192, 8192, dtype=torch.float64, device=tdev); b = torch.randn_like(a); c = torch.empty_like(a)
+        torch.matmul(a, b, out=c); torch.cuda.synchronize()
+        c0, c1 = ev(), ev(); c0.record(); torch.matmul(a, b, out=c); c1.record(); torch.cuda.synchronize()
+        cublas_tf = 2 * 8192 ** 3 / c0.elapsed_time(c1) / 1e9
+        del a, b, c
+        med = {kk: statistics.median(vv) for kk, vv in phase_ms.items()}
+        score_ms = med["score"]
+        achieved = fl["score"] / (score_ms * 1e-3) / 1e12
+        phases = {
+            "assemble_src": {"ms": med["assemble_src"], "GBps": n1 * A1.stride(0) * 8 / med["assemble_src"] / 1e6},
+            "potrf_src": {"ms": med["potrf_src"], "tflops": n1 ** 3 / 3 / med["potrf_src"] / 1e9},
+            "trtri_src": {"ms": med["trtri_src"], "tflops": n1 ** 3 / 3 / med["trtri_src"] / 1e9},
+            "assemble_tgt": {"ms": med["assemble_tgt"], "GBps": n2 * A2.stride(0) * 8 / med["assemble_tgt"] / 1e6},
+            "potrf_tgt": {"ms": med["potrf_tgt"], "tflops": n2 ** 3 / 3 / med["potrf_tgt"] / 1e9},
+            "trtri_tgt": {"ms": med["trtri_tgt"], "tflops": n2 ** 3 / 3 / med["trtri_tgt"] / 1e9},
+            "embed": {"ms": med["embed"], "tflops": (fl["rows"] + fl["gram"] + fl["solve"] + fl["proj"]) / med["embed"] / 1e9},
+            "score": {"ms": score_ms, "tflops": achieved},
+        }
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: source %d / target %d nodes, %d landmarks, lam 0.05, Barabasi-Albert m=10 "
+                                   "(seeds 1+2r/2+2r), one graph pair per GPU" % (args.config, n1, n2, k),
+                       "parallelism": "1 GPU" if world == 1 else "replicas: one independent graph pair per GPU, no collective",
+                       "l2": "inputs larger than L2: %.1f GB of FP64 matrices per step vs 126 MB L2" % (
+                           (n1 * n1 + n2 * n2 + 2 * n1 * n2) * 8 / 1e9),
+                       "useful_tflop_per_step": fl["total"] / 1e12, "seconds_per_pipeline": ms_step * 1e-3},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "note": "edge/index arrays H2D from pinned memory; C1, C2hat^T and S D2H into pinned memory"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
+                         "frac": achieved / dmma_peak, "traffic": None,
+                         "kernel": "dgemm_dmma_tma_kernel<MC,MC> score launch: S = W1^T P, %d x %d x %d, "
+                                   "k >= row only (%.2f TFLOP)" % (n1, n2, n1, fl["score"] / 1e12),
+                         "peak_source": "measured in this run: FP64 DMMA issue-rate microbenchmark "
+                                        "(MEASURED_PEAKS.json has no FP64 entry); cuBLAS dgemm 8192^3 = %.2f TFLOP/s; "
+                                        "vendor FP64 peak 37-40 TFLOP/s" % cublas_tf,
+                         "cublas_dgemm_tflops": cublas_tf,
+                         "hbm_peak_gbs": peaks.get("hbm_gbs")},
+            "phases": phases,
+            "counted_tile_flops_per_step": counted_flops / args.steps,
+        }
+        if not args.no_cpu and world == 1:
+            info = cpu_info()
+            tf, secs, desc = cpu_sample(args.config, args.cpu_n1, args.cpu_n2)
+            line["cpu_baseline"] = {"value": tf, "unit": UNIT, "cores": info.get("threads"), "kind": "port",
+                                    "sample": desc, "host": info}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--impl", default="munk_b200", choices=["munk_b200", "reference"])
+    ap.add_argument("--cpu-n1", dest="cpu_n1", type=int, default=3000)
+    ap.add_argument("--cpu-n2", dest="cpu_n2", type=int, default=2400)
+    ap.add_argument("--cpu-max-steps", dest="cpu_max_steps", type=int, default=5)
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

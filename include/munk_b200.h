@@ -111,6 +111,33 @@ int munk_group_mean_rows(int ngroups, const int* gptr, const int* members, int n
 int munk_gather_pairs(int npairs, const int* r, const int* c, const double* S, long lds,
                       double* out, void* stream);
 
+/* out = tril(in): the lower factor with exact zeros above the diagonal (n x n). */
+int munk_copy_lower(int n, const double* in, long ldi, double* out, long ldo, void* stream);
+
+/*
+ * separate_scores (munk/munk/munk.py:20-68) as one streaming pass over S (n1 x n2).  The host
+ * derives from the integer index lists: rowL/colL (landmark row / column flags), colrank[j] =
+ * number of landmark columns before j, the landmark-pair cells and the H_H cells (homolog
+ * pairs minus landmark pairs) as CSR over rows with ascending columns, and for each row the
+ * offset of its first element in each output.  Outputs are in the reference's row-major mask
+ * order.  (L_L_diag and H_H themselves are munk_gather_pairs over the index lists.)
+ */
+int munk_separate_scores(int n1, int n2, const double* S, long lds, const unsigned char* rowL,
+                         const unsigned char* colL, const int* colrank, const int* p_ptr,
+                         const int* p_col, const int* h_ptr, const int* h_col,
+                         const long* off_lloff, const long* off_lnonl, const long* off_other,
+                         double* out_lloff, double* out_lnonl, double* out_other, void* stream);
+
+/*
+ * out5 = {mean(H_H), mean(other), mean(H_H) - mean(other), |H_H|, |other|} without materialising
+ * the selections (permtest.py:58-66 dissim_diff).  h_row/h_col list the nh H_H cells;
+ * n_other = |other| (host integer arithmetic); rowsum_scratch holds n1 doubles.
+ */
+int munk_separate_scores_means(int n1, int n2, const double* S, long lds,
+                               const unsigned char* rowL, const unsigned char* colL, int nh,
+                               const int* h_row, const int* h_col, double n_other,
+                               double* rowsum_scratch, double* out5, void* stream);
+
 /* Micro-benchmarks used by bench.py / tools to measure the FP64 ceilings of the box.
  * Each runs on `device`, blocks, and returns TFLOP/s in *tflops. */
 int munk_microbench_dmma(int device, int iters, double* tflops);

@@ -1,0 +1,19 @@
+"""munk_b200 — MUNK's dense linear-algebra hot path on NVIDIA B200 (sm_100a).
+
+Drop-in for the reference `munk` package (munk/munk/__init__.py:1-11): same exported names.
+The CUDA library (munk_b200/lib/libmunk_b200.so, C ABI in include/munk_b200.h) must be built
+(`python -m munk_b200.build`); importing the package without it fails — there is no CPU path.
+"""
+from . import util
+from . import io
+from .munk import (
+    separate_scores,
+    regularized_laplacian,
+    rkhs_factor,
+    embed_matrices,
+    embed_networks,
+    save_embeddings,
+    scores,
+)
+
+__version__ = '0.1'

@@ -35,13 +35,11 @@ SIGNATURES = {
     "munk_group_mean_rows": (c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_long, c_void_p,
                                      c_long, c_void_p]),
     "munk_gather_pairs": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_long, c_void_p, c_void_p]),
-    "munk_separate_scores_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
-                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "munk_separate_scores": (c_int, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p]),
-    "munk_separate_scores_means": (c_int, [c_void_p, c_int, c_int, c_void_p, c_long, c_void_p,
-                                           c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "munk_copy_lower": (c_int, [c_int, c_void_p, c_long, c_void_p, c_long, c_void_p]),
+    "munk_separate_scores": (c_int, [c_int, c_int, c_void_p, c_long] + [c_void_p] * 13 + [c_void_p]),
+    "munk_separate_scores_means": (c_int, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_int,
+                                           c_void_p, c_void_p, c_double, c_void_p, c_void_p,
+                                           c_void_p]),
     "munk_microbench_dmma": (c_int, [c_int, c_int, _P(c_double)]),
     "munk_microbench_dfma": (c_int, [c_int, c_int, _P(c_double)]),
 }

@@ -151,6 +151,10 @@ int munk_transpose_lower(int n, const double* W, long ldw, double* C, long ldc, 
   return transpose_lower(n, W, ldw, C, ldc, S(stream));
 }
 
+int munk_copy_lower(int n, const double* in, long ldi, double* out, long ldo, void* stream) {
+  return copy_lower(n, in, ldi, out, ldo, S(stream));
+}
+
 int munk_group_mean_rows(int ngroups, const int* gptr, const int* members, int ncols,
                          const double* in, long ldi, double* out, long ldo, void* stream) {
   return group_mean_rows(ngroups, gptr, members, ncols, in, ldi, out, ldo, S(stream));

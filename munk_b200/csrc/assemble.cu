@@ -84,6 +84,13 @@ __global__ void transpose_lower_kernel(int n, const double* __restrict__ in, lon
   }
 }
 
+__global__ void copy_lower_kernel(int n, const double* __restrict__ in, long ldi,
+                                  double* __restrict__ out, long ldo) {
+  const int r = blockIdx.x;
+  for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < n; c += gridDim.y * blockDim.x)
+    out[(long)r * ldo + c] = (c <= r) ? in[(long)r * ldi + c] : 0.0;
+}
+
 // out[g][j] = mean over l in group g of in[members[l]][j]
 __global__ void group_mean_rows_kernel(int ngroups, const int* __restrict__ gptr,
                                        const int* __restrict__ members, int ncols,
@@ -143,6 +150,14 @@ int transpose_lower(int n, const double* in, long ldi, double* out, long ldo, cu
   if (n <= 0) return MUNK_OK;
   dim3 grid((n + 31) / 32, (n + 31) / 32);
   transpose_lower_kernel<<<grid, dim3(32, 8), 0, stream>>>(n, in, ldi, out, ldo);
+  MUNK_CUDA_TRY(cudaGetLastError());
+  return MUNK_OK;
+}
+
+int copy_lower(int n, const double* in, long ldi, double* out, long ldo, cudaStream_t stream) {
+  if (n <= 0) return MUNK_OK;
+  dim3 grid(n, std::min(16, (n + 255) / 256));
+  copy_lower_kernel<<<grid, 256, 0, stream>>>(n, in, ldi, out, ldo);
   MUNK_CUDA_TRY(cudaGetLastError());
   return MUNK_OK;
 }

@@ -1,0 +1,266 @@
+"""Device layer: the MUNK hot path as calls into libmunk_b200.so on CUDA tensors.
+
+torch is used only as plumbing (device memory, streams, pinned host buffers); every kernel is
+ours and is reached through the C ABI in include/munk_b200.h.  All device matrices are row-major
+float64 with a padded leading dimension (multiple of 16 elements = 128 bytes, so TMA box rows
+are line-aligned).
+
+Factor convention: for an SPD matrix A = L L^T we keep W = L^-1 (lower triangular).  Then
+D = A^-1 = W^T W, and C = W^T is the RKHS factor (C C^T = D) that replaces the reference's
+eigendecomposition (munk/munk/munk.py:85-88).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import MunkError, check, lib
+
+# structure flags of munk_dgemm (include/munk_b200.h)
+KC, MC = 0, 1
+TILE_LOWER, KLO_M, KLO_N, KHI_M, KHI_N, SYM_MIRROR = 1, 2, 4, 8, 16, 32
+
+
+class NotPositiveDefinite(np.linalg.LinAlgError):
+    pass
+
+
+def pad16(n):
+    return (int(n) + 15) // 16 * 16
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Device:
+    """One CUDA device + the library workspace bound to torch's current stream on it."""
+
+    def __init__(self, index=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("munk_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.index = torch.cuda.current_device() if index is None else int(index)
+        self.torch_device = torch.device("cuda", self.index)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.index):
+            check(lib.munk_workspace_create(self.index, ctypes.byref(handle)), "munk_workspace_create")
+        self._ws = handle
+
+    def __del__(self):
+        ws = getattr(self, "_ws", None)
+        if ws:
+            try:
+                lib.munk_workspace_destroy(ws)
+            except Exception:
+                pass
+            self._ws = None
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.index).cuda_stream)
+
+    def empty(self, rows, cols, ld=None):
+        """(rows x ld) buffer; the logical matrix is [:, :cols]."""
+        ld = pad16(cols) if ld is None else ld
+        return torch.empty((int(rows), int(ld)), dtype=torch.float64, device=self.torch_device)
+
+    def ints(self, values):
+        arr = np.ascontiguousarray(np.asarray(values, dtype=np.int32))
+        return torch.from_numpy(arr).to(self.torch_device, non_blocking=False)
+
+    def stats(self, reset=False):
+        launches, flops = ctypes.c_long(), ctypes.c_double()
+        check(lib.munk_workspace_stats(self._ws, ctypes.byref(launches), ctypes.byref(flops),
+                                       1 if reset else 0), "munk_workspace_stats")
+        return launches.value, flops.value
+
+    def upload(self, array, cols=None):
+        """Host (rows x cols) float64 array -> padded device buffer."""
+        a = np.asarray(array, dtype=np.float64)
+        rows, cols = a.shape
+        buf = self.empty(rows, cols)
+        if buf.shape[1] != cols:
+            buf[:, cols:].zero_()
+        buf[:, :cols].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        return buf
+
+    def download(self, buf, rows, cols, out=None):
+        """Device [:rows, :cols] -> host ndarray (through a pinned staging tensor)."""
+        host = out if out is not None else torch.empty((rows, cols), dtype=torch.float64, pin_memory=True)
+        host.copy_(buf[:rows, :cols], non_blocking=True)
+        torch.cuda.current_stream(self.index).synchronize()
+        return host.numpy()
+
+    # ---- kernels ----------------------------------------------------------------------------
+    def gemm(self, a_layout, b_layout, M, N, K, alpha, A, B, beta, C, flags=0):
+        check(lib.munk_dgemm(self._ws, a_layout, b_layout, M, N, K, alpha, _ptr(A), A.stride(0),
+                             _ptr(B), B.stride(0), beta, _ptr(C), C.stride(0), flags, self.stream()),
+              "munk_dgemm")
+
+    def assemble(self, n, edges_u, edges_v, lam, out=None):
+        """A = I + lam*L from int32 edge index arrays (host or device)."""
+        u = edges_u if torch.is_tensor(edges_u) else self.ints(edges_u)
+        v = edges_v if torch.is_tensor(edges_v) else self.ints(edges_v)
+        A = self.empty(n, n) if out is None else out
+        check(lib.munk_assemble_reglap(self._ws, n, int(u.numel()), _ptr(u), _ptr(v), float(lam),
+                                       _ptr(A), A.stride(0), self.stream()), "munk_assemble_reglap")
+        return A
+
+    def new_linv(self, n):
+        return torch.empty(lib.munk_linv_bytes(int(n)) // 8, dtype=torch.float64, device=self.torch_device)
+
+    def potrf(self, A, n, linv=None, check_info=True):
+        """In-place lower Cholesky; returns the leaf-inverse buffer trtri needs."""
+        linv = self.new_linv(n) if linv is None else linv
+        check(lib.munk_potrf(self._ws, n, _ptr(A), A.stride(0), _ptr(linv), self.stream()), "munk_potrf")
+        if check_info:
+            self.raise_if_not_spd()
+        return linv
+
+    def potrf_info(self):
+        info = ctypes.c_int(0)
+        check(lib.munk_potrf_info(self._ws, ctypes.byref(info), self.stream()), "munk_potrf_info")
+        return info.value
+
+    def raise_if_not_spd(self):
+        info = self.potrf_info()
+        if info:
+            raise NotPositiveDefinite("matrix is not positive definite (pivot %d)" % (info - 1))
+
+    def trtri(self, L, n, linv):
+        check(lib.munk_trtri(self._ws, n, _ptr(L), L.stride(0), _ptr(linv), self.stream()), "munk_trtri")
+        return L
+
+    def inverse_factor(self, A, n, check_info=True):
+        """A (SPD, overwritten) -> W = chol(A)^-1, lower triangular, in place."""
+        linv = self.potrf(A, n, check_info=check_info)
+        return self.trtri(A, n, linv)
+
+    def gram_lower(self, W, n, out=None, ld=None):
+        """D = W^T W (full symmetric)."""
+        D = self.empty(n, n, ld) if out is None else out
+        check(lib.munk_gram_lower(self._ws, n, _ptr(W), W.stride(0), _ptr(D), D.stride(0), self.stream()),
+              "munk_gram_lower")
+        return D
+
+    def gather_cols_lower(self, W, n, idx):
+        """Q (n x pad16(k)) with Q[:, l] = column idx[l] of the lower-triangular W."""
+        idx_d = idx if torch.is_tensor(idx) else self.ints(idx)
+        k = int(idx_d.numel())
+        Q = self.empty(n, k)
+        check(lib.munk_gather_cols_lower(n, _ptr(W), W.stride(0), k, _ptr(idx_d), _ptr(Q), Q.stride(0),
+                                         self.stream()), "munk_gather_cols_lower")
+        return Q
+
+    def transpose_lower(self, W, n, ld=None):
+        C = self.empty(n, n, ld)
+        check(lib.munk_transpose_lower(n, _ptr(W), W.stride(0), _ptr(C), C.stride(0), self.stream()),
+              "munk_transpose_lower")
+        return C
+
+    def copy_lower(self, L, n, ld=None):
+        out = self.empty(n, n, ld)
+        check(lib.munk_copy_lower(n, _ptr(L), L.stride(0), _ptr(out), out.stride(0), self.stream()),
+              "munk_copy_lower")
+        return out
+
+    def group_mean_rows(self, B, ncols, gptr, members):
+        g = len(gptr) - 1
+        out = self.empty(g, ncols)
+        gp, mem = self.ints(gptr), self.ints(members)
+        check(lib.munk_group_mean_rows(g, _ptr(gp), _ptr(mem), ncols, _ptr(B), B.stride(0), _ptr(out),
+                                       out.stride(0), self.stream()), "munk_group_mean_rows")
+        return out
+
+    def gather_pairs(self, S, rows, cols):
+        r, c = self.ints(rows), self.ints(cols)
+        out = torch.empty(int(r.numel()), dtype=torch.float64, device=self.torch_device)
+        check(lib.munk_gather_pairs(int(r.numel()), _ptr(r), _ptr(c), _ptr(S), S.stride(0), _ptr(out),
+                                    self.stream()), "munk_gather_pairs")
+        return out
+
+    # ---- the hot path, device resident -------------------------------------------------------
+    def kernel_factor(self, n, edges_u, edges_v, lam):
+        """W with D = (I + lam L)^-1 = W^T W  (assembly + Cholesky + triangular inverse)."""
+        A = self.assemble(n, edges_u, edges_v, lam)
+        return self.inverse_factor(A, n)
+
+    def spd_solve_gram(self, G, k, B, ncols):
+        """Z = G^-1 B for the small SPD k x k Gram matrix (overwritten).  Raises
+        NotPositiveDefinite if a pivot of the Cholesky factorisation is not positive."""
+        Wg = self.inverse_factor(G, k)
+        Y = self.empty(k, ncols)
+        self.gemm(KC, MC, k, ncols, k, 1.0, Wg, B, 0.0, Y, KHI_M)      # Y = Wg B
+        Z = self.empty(k, ncols)
+        self.gemm(MC, MC, k, ncols, k, 1.0, Wg, Y, 0.0, Z, KLO_M)      # Z = Wg^T Y
+        return Z
+
+    def project(self, Q1, n1, B, n2, groups):
+        """P = C2hat^T = pinv(M) B with M^T = Q1 (n1 x k'), B = D2[Lt,:] (k x n2).
+
+        `groups` = (gptr, members) folds rows of B that belong to the same (duplicated) source
+        landmark: np.linalg.pinv's least-squares / minimum-norm answer for duplicate rows of M
+        equals the answer for the de-duplicated M with the rows of B averaged.  With distinct
+        rows M M^T = D1[Ls,Ls] is a principal submatrix of an SPD matrix, so it is SPD with
+        condition <= cond(D1) and the Gram/Cholesky route is the exact pinv.
+        """
+        gptr, members = groups
+        kq = len(gptr) - 1
+        if any(gptr[g + 1] - gptr[g] != 1 for g in range(kq)) or list(members) != list(range(kq)):
+            B = self.group_mean_rows(B, n2, gptr, members)
+        G = self.empty(kq, kq)
+        self.gemm(MC, MC, kq, kq, n1, 1.0, Q1, Q1, 0.0, G, 0)          # G = M M^T
+        Z = self.spd_solve_gram(G, kq, B, n2)
+        P = self.empty(n1, n2)
+        self.gemm(KC, MC, n1, n2, kq, 1.0, Q1, Z, 0.0, P, 0)           # P = M^T Z
+        return P
+
+    def target_landmark_rows(self, W2, n2, target_idx):
+        """B = D2[Lt, :] = (W2[:, Lt])^T W2 without forming D2 (k x n2)."""
+        Q2 = self.gather_cols_lower(W2, n2, target_idx)
+        k = len(target_idx)
+        B = self.empty(k, n2)
+        self.gemm(MC, MC, k, n2, n2, 1.0, Q2, W2, 0.0, B, KLO_N)
+        return B
+
+    def score(self, W1, n1, P, n2, out=None, ld=None):
+        """S = C1 C2hat^T = W1^T P; only k >= row of the triangular W1 is contracted."""
+        S = self.empty(n1, n2, ld) if out is None else out
+        self.gemm(MC, MC, n1, n2, n1, 1.0, W1, P, 0.0, S, KLO_M)
+        return S
+
+
+def landmark_groups(source_idx):
+    """First-occurrence de-duplication of the source landmark list.
+
+    Returns (unique_source_idx, gptr, members): group g collects the positions l of
+    source_idx with source_idx[l] == unique_source_idx[g], in list order.
+    """
+    first = {}
+    buckets = []
+    for pos, s in enumerate(source_idx):
+        g = first.get(s)
+        if g is None:
+            first[s] = len(buckets)
+            buckets.append([pos])
+        else:
+            buckets[g].append(pos)
+    uniq = [source_idx[b[0]] for b in buckets]
+    gptr = [0]
+    members = []
+    for b in buckets:
+        members.extend(b)
+        gptr.append(len(members))
+    return uniq, gptr, members
+
+
+_default = {}
+
+
+def default_device(index=None):
+    """Process-wide Device per CUDA ordinal (created on first use)."""
+    idx = torch.cuda.current_device() if index is None else int(index)
+    dev = _default.get(idx)
+    if dev is None:
+        dev = _default[idx] = Device(idx)
+    return dev

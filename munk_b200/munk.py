@@ -1,0 +1,144 @@
+"""The `munk` package API on B200 (reference: munk/munk/munk.py, munk/munk/__init__.py:3-9).
+
+Same names, arguments, return shapes and error behaviour as the reference; the arithmetic runs
+in hand-written sm_100a kernels behind include/munk_b200.h.  Inputs and outputs at this level
+are host numpy arrays (the reference's contract); `munk_b200.pipeline` keeps everything on the
+device for callers that chain the stages.
+"""
+import joblib
+import numpy as np
+import torch
+
+from . import util
+from .device import KC, MC, default_device, landmark_groups, NotPositiveDefinite
+from .pipeline import embed_device, graph_inputs
+from .scores_plan import plan_separate_scores
+
+
+def regularized_laplacian(G, nodes, lam):
+    """D = (I + lam L)^-1 for the node order `nodes` (munk.py:74-83), dense float64 (n, n).
+
+    Computed as W^T W with W = chol(I + lam L)^-1: the matrix is SPD for lam >= 0, so the LU
+    solve of np.linalg.inv is replaced by a Cholesky factorisation and a triangular inverse.
+    Raises numpy.linalg.LinAlgError if I + lam L is not positive definite.
+    """
+    n = len(nodes)
+    if n == 0:
+        return np.empty((0, 0))
+    dev = default_device()
+    u, v = util.edge_index_arrays(G, nodes)
+    W = dev.kernel_factor(n, u, v, lam)
+    D = dev.gram_lower(W, n, ld=n + (n & 1))
+    return dev.download(D, n, n)
+
+
+def rkhs_factor(D):
+    """C with C C^T = D (munk.py:85-88).
+
+    The reference returns V diag(sqrt(e)) from an eigendecomposition; any factor differs from
+    it by an orthogonal matrix on the right and gives the same kernel and the same MUNK scores,
+    so the Cholesky factor (lower triangular) is returned.  Like scipy.linalg.eigh, only the
+    lower triangle of D is read.  Raises numpy.linalg.LinAlgError if D is not positive definite.
+    """
+    D = np.asarray(D, dtype=np.float64)
+    n = D.shape[0]
+    if D.ndim != 2 or D.shape[1] != n:
+        raise ValueError("expected square matrix")
+    if n == 0:
+        return np.empty((0, 0))
+    dev = default_device()
+    A = dev.upload(D)
+    dev.potrf(A, n)
+    C = dev.copy_lower(A, n, ld=n + (n & 1))
+    return dev.download(C, n, n)
+
+
+def non_landmark_idxs(n, landmark_idxs):
+    """munk.py:90-91 (no caller in the reference; kept for API completeness)."""
+    skip = set(landmark_idxs)
+    return [i for i in range(n) if i not in skip]
+
+
+def embed_matrices(source_C, target_D, landmark_idxs):
+    """C2hat = (pinv(C1[Ls,:]) . D2[Lt,:]).T  (munk.py:97-112); returns (source_C, C2hat).
+
+    `source_C` is returned as the same object and C2hat as an (n2, d) transposed view, like the
+    reference.  Only the k landmark rows of either input are uploaded.  The pseudo-inverse is
+    the exact minimum-norm least-squares operator when the distinct landmark rows of C1 are
+    linearly independent (always true for rows of a kernel factor); repeated source landmarks
+    are folded exactly.  Otherwise numpy.linalg.LinAlgError is raised.
+    """
+    s_idx, t_idx = zip(*landmark_idxs)
+    C = np.asarray(source_C)
+    D2 = np.asarray(target_D)
+    dev = default_device()
+    uniq, gptr, members = landmark_groups([int(s) for s in s_idx])
+    d, n2 = C.shape[1], D2.shape[1]
+    Q1 = dev.upload(np.ascontiguousarray(C[uniq, :].T))            # d x k'
+    B = dev.upload(D2[[int(t) for t in t_idx], :])                  # k x n2
+    P = dev.project(Q1, d, B, n2, (gptr, members))
+    return source_C, dev.download(P, d, n2).T
+
+
+def scores(source_X, target_X):
+    """S = source_X . target_X^T on the GPU (scripts/compute_embeddings.py:81 np.dot,
+    permtest.py:55 `@`).  Host arrays in, host (n1, n2) array out."""
+    X1 = np.asarray(source_X, dtype=np.float64)
+    X2 = np.asarray(target_X, dtype=np.float64)
+    n1, d = X1.shape
+    n2 = X2.shape[0]
+    dev = default_device()
+    A = dev.upload(X1)
+    if X2.flags.f_contiguous and not X2.flags.c_contiguous:
+        B = dev.upload(X2.T)                                        # stored (d, n2): free index contiguous
+        b_layout = MC
+    else:
+        B = dev.upload(X2)
+        b_layout = KC
+    S = dev.empty(n1, n2, ld=n2 + (n2 & 1))
+    dev.gemm(KC, b_layout, n1, n2, d, 1.0, A, B, 0.0, S, 0)
+    return dev.download(S, n1, n2)
+
+
+def embed_networks(source_G, target_G, homologs, n_landmarks,
+                   src_lam=0.05, tgt_lam=0.05, return_idxs=False):
+    """MUNK embeddings of two graphs (munk.py:114-176); same two return shapes.
+
+    ((source_C, source_nodes), (target_C_hat, target_nodes), landmark_homs, runtimes) or, with
+    return_idxs, (..., landmark_idxs, homolog_idxs).  source_C = W^T is upper triangular (see
+    rkhs_factor); compare with the reference after orthogonal Procrustes alignment.
+    """
+    inp = graph_inputs(source_G, target_G, homologs, n_landmarks)
+    emb = embed_device(len(inp["source_nodes"]), inp["edges1"], len(inp["target_nodes"]),
+                       inp["edges2"], inp["landmark_idxs"], src_lam, tgt_lam)
+    source_C = emb.source_C()
+    target_C_hat = emb.target_C_hat()
+    if return_idxs:
+        s_pos, t_pos = inp["s_pos"], inp["t_pos"]
+        homolog_idxs = [(s_pos[a], t_pos[b]) for a, b in homologs]
+        return ((source_C, inp["source_nodes"]), (target_C_hat, inp["target_nodes"]),
+                inp["landmark_idxs"], homolog_idxs)
+    return ((source_C, inp["source_nodes"]), (target_C_hat, inp["target_nodes"]),
+            inp["landmark_homs"], emb.runtimes)
+
+
+def separate_scores(scores, landmark_pair_idxs, homolog_pair_idxs):
+    """The five score groups of munk.py:20-68, each in the reference's row-major mask order:
+    landmark pairs, landmark-landmark off-diagonal, landmark x non-landmark, homolog pairs
+    (landmark pairs removed), everything else.  `scores` may be a host array or a CUDA tensor."""
+    dev = default_device()
+    if torch.is_tensor(scores):
+        S, (n1, n2) = scores, (scores.shape[0], scores.shape[1])
+        if S.stride(1) != 1:
+            raise ValueError("device scores must be row-major")
+    else:
+        host = np.asarray(scores, dtype=np.float64)
+        n1, n2 = host.shape
+        S = torch.from_numpy(np.ascontiguousarray(host)).to(dev.torch_device)
+    plan = plan_separate_scores(n1, n2, landmark_pair_idxs, homolog_pair_idxs)
+    return plan.run(dev, S)
+
+
+def save_embeddings(X, nodes, landmarks, fp, weight=None):
+    """joblib pickle of dict(X, nodes, landmarks, weight) (munk.py:178-180)."""
+    joblib.dump(dict(X=X, nodes=nodes, landmarks=landmarks, weight=weight), fp)

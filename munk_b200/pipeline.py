@@ -1,0 +1,130 @@
+"""Device-resident MUNK pipeline: graphs + homolog index pairs -> C1, C2hat, scores on one GPU.
+
+This is what `embed_networks` (munk/munk/munk.py:114-176) followed by the score product
+(scripts/compute_embeddings.py:81) computes, restructured so that nothing round-trips through
+the host between the stages:
+
+    W1 = chol(I + lam L1)^-1, W2 = chol(I + lam L2)^-1          (C1 = W1^T, D2 = W2^T W2)
+    Q1 = W1[:, Ls']  (= C1[Ls',:]^T, duplicates of Ls folded)    B = D2[Lt,:] = W2[:,Lt]^T W2
+    P  = C2hat^T = Q1 (Q1^T Q1)^-1 mean_groups(B)               S = W1^T P
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import util
+from .device import default_device, landmark_groups
+
+
+class PhaseTimer:
+    """Wall-clock phase timers bracketed by a stream synchronise (reference keys,
+    munk/munk/munk.py:161-164)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.times = {}
+
+    def __call__(self, key):
+        return _Phase(self, key)
+
+
+class _Phase:
+    def __init__(self, owner, key):
+        self.owner, self.key = owner, key
+
+    def __enter__(self):
+        torch.cuda.current_stream(self.owner.dev.index).synchronize()
+        self.t0 = time.time()
+
+    def __exit__(self, *exc):
+        torch.cuda.current_stream(self.owner.dev.index).synchronize()
+        self.owner.times[self.key] = self.owner.times.get(self.key, 0.0) + time.time() - self.t0
+        return False
+
+
+class DeviceEmbedding:
+    """Result of embed_device(): everything still on the GPU."""
+
+    def __init__(self, dev, n1, n2, W1, W2, P, runtimes):
+        self.dev, self.n1, self.n2 = dev, n1, n2
+        self.W1, self.W2, self.P = W1, W2, P
+        self.runtimes = runtimes
+        self._S = None
+
+    def scores(self):
+        if self._S is None:
+            self._S = self.dev.score(self.W1, self.n1, self.P, self.n2)
+        return self._S
+
+    # host copies (API edge)
+    def source_C(self):
+        C = self.dev.transpose_lower(self.W1, self.n1)
+        return self.dev.download(C, self.n1, self.n1)
+
+    def target_C_hat(self):
+        # (n2, n1) transposed view of the (n1, n2) array, exactly as munk.py:109-110 returns it
+        return self.dev.download(self.P, self.n1, self.n2).T
+
+    def scores_host(self):
+        return self.dev.download(self.scores(), self.n1, self.n2)
+
+
+def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.05, dev=None,
+                 keep_target_factor=True):
+    """Hot path on index data: edges as (u, v) int32 arrays in sorted-node order, landmark_idxs
+    as [(source_row, target_row)].  Returns a DeviceEmbedding."""
+    dev = dev or default_device()
+    timer = PhaseTimer(dev)
+    s_idx = [int(a) for a, _ in landmark_idxs]
+    t_idx = [int(b) for _, b in landmark_idxs]
+    uniq, gptr, members = landmark_groups(s_idx)
+
+    with timer("source_regularized_laplacian_runtime"):
+        A1 = dev.assemble(n1, edges1[0], edges1[1], src_lam)
+        linv1 = dev.potrf(A1, n1)
+    with timer("source_rkhs_factorization_runtime"):
+        W1 = dev.trtri(A1, n1, linv1)
+        del linv1
+    with timer("target_regularized_laplacian_runtime"):
+        A2 = dev.assemble(n2, edges2[0], edges2[1], tgt_lam)
+        W2 = dev.inverse_factor(A2, n2)
+    with timer("embed_runtime"):
+        Q1 = dev.gather_cols_lower(W1, n1, uniq)
+        B = dev.target_landmark_rows(W2, n2, t_idx)
+        P = dev.project(Q1, n1, B, n2, (gptr, members))
+        dev.raise_if_not_spd()
+    return DeviceEmbedding(dev, n1, n2, W1, W2 if keep_target_factor else None, P, timer.times)
+
+
+def graph_inputs(source_G, target_G, homologs, n_landmarks):
+    """Bit-exact host side of embed_networks: node order, index maps, landmark selection
+    (munk/munk/munk.py:129-154,167-168)."""
+    assert n_landmarks <= len(homologs)
+    source_nodes = util.sorted_nodes(source_G)
+    target_nodes = util.sorted_nodes(target_G)
+    s_pos = {name: i for i, name in enumerate(source_nodes)}
+    t_pos = {name: i for i, name in enumerate(target_nodes)}
+    landmark_homs = homologs[:n_landmarks]
+    landmark_idxs = [(s_pos[a], t_pos[b]) for a, b in landmark_homs]
+    edges1 = util.edge_index_arrays(source_G, source_nodes)
+    edges2 = util.edge_index_arrays(target_G, target_nodes)
+    return dict(source_nodes=source_nodes, target_nodes=target_nodes, s_pos=s_pos, t_pos=t_pos,
+                landmark_homs=landmark_homs, landmark_idxs=landmark_idxs, edges1=edges1, edges2=edges2)
+
+
+def embed_and_score(source_G, target_G, homologs, n_landmarks, src_lam=0.05, tgt_lam=0.05, dev=None):
+    """Everything the CLI needs in one device-resident pass.
+
+    Returns dict(source_X, target_X, scores, source_nodes, target_nodes, landmarks, runtimes).
+    """
+    inp = graph_inputs(source_G, target_G, homologs, n_landmarks)
+    emb = embed_device(len(inp["source_nodes"]), inp["edges1"], len(inp["target_nodes"]), inp["edges2"],
+                       inp["landmark_idxs"], src_lam, tgt_lam, dev=dev, keep_target_factor=False)
+    t0 = time.time()
+    S = emb.scores_host()
+    runtimes = dict(emb.runtimes)
+    score_time = time.time() - t0
+    return dict(source_X=emb.source_C(), target_X=emb.target_C_hat(), scores=S,
+                source_nodes=inp["source_nodes"], target_nodes=inp["target_nodes"],
+                landmarks=inp["landmark_homs"], runtimes=runtimes, score_runtime=score_time)

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""MUNK embeddings + similarity scores from two edge lists and a homolog list, on a B200.
+
+Drop-in for the reference CLI (scripts/compute_embeddings.py:17-31 flag surface, :72-98 output
+files and schemas).  The numeric work (both regularized-Laplacian kernels, the source RKHS
+factor, the landmark projection and the n1 x n2 score product) runs in one device-resident
+pass (munk_b200.pipeline.embed_and_score); only the three result matrices come back to the host.
+"""
+import argparse
+import json
+import os
+import random
+import sys
+import time
+
+import joblib
+import networkx as nx
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+
+import munk_b200 as munk  # noqa: E402
+from munk_b200 import pipeline, util  # noqa: E402
+
+REQUIRED = [
+    ('-se', '--source_edgelist'), ('-te', '--target_edgelist'), ('-hf', '--homolog_list'),
+    ('-so', '--source_output_file'), ('-to', '--target_output_file'),
+    ('-sim', '--sim_scores_output_file'), ('-lo', '--landmarks_output_file'),
+    ('-r', '--runtimes_file'),
+]
+
+
+def build_parser():
+    ap = argparse.ArgumentParser(description=__doc__.splitlines()[0])
+    for short, long_name in REQUIRED:
+        ap.add_argument(short, long_name, type=str, required=True)
+    ap.add_argument('-n', '--n_landmarks', type=int, default=400)
+    ap.add_argument('-rs', '--random_seed', type=int, default=28791)
+    ap.add_argument('--src_lam', type=float, default=0.05)
+    ap.add_argument('--tgt_lam', type=float, default=0.05)
+    return ap
+
+
+def load_two_core(path, log, what):
+    log.info('Loading %s edgelist from %s', what, path)
+    return util.simple_two_core(nx.read_edgelist(path, encoding='ascii'))
+
+
+def run(args):
+    log = munk.io.get_logger()
+    random.seed(args.random_seed)   # accepted for compatibility; landmarks are the first k pairs
+
+    log.info('Loading homologs list from %s', args.homolog_list)
+    raw_homologs = util.read_homolog_list(args.homolog_list)
+    source_G = load_two_core(args.source_edgelist, log, 'source')
+    target_G = load_two_core(args.target_edgelist, log, 'target')
+    homologs = util.homologs_in_graphs(source_G, target_G, raw_homologs)
+
+    log.info('Computing MUNK embeddings with %d landmarks', args.n_landmarks)
+    started = time.time()
+    res = pipeline.embed_and_score(source_G, target_G, homologs, args.n_landmarks,
+                                   src_lam=args.src_lam, tgt_lam=args.tgt_lam)
+    total_time = time.time() - started
+    landmarks = res['landmarks']
+
+    log.info('Saving source species embeddings to %s', args.source_output_file)
+    munk.save_embeddings(res['source_X'], res['source_nodes'], [a for a, _ in landmarks],
+                         args.source_output_file)
+    log.info('Saving target species embeddings to %s', args.target_output_file)
+    munk.save_embeddings(res['target_X'], res['target_nodes'], [b for _, b in landmarks],
+                         args.target_output_file)
+    log.info('Source data shape {}'.format(res['source_X'].shape))
+    log.info('Target data shape {}'.format(res['target_X'].shape))
+
+    log.info('Saving MUNK similarity scores to %s', args.sim_scores_output_file)
+    joblib.dump(dict(X=res['scores'], A_nodes=res['source_nodes'], B_nodes=res['target_nodes'],
+                     landmarks=landmarks, homologs=homologs), args.sim_scores_output_file)
+
+    log.info('Saving landmark list to %s', args.landmarks_output_file)
+    with open(args.landmarks_output_file, 'w') as out:
+        out.writelines('%s\t%s\n' % pair for pair in landmarks)
+
+    log.info('Saving runtimes to %s', args.runtimes_file)
+    with open(args.runtimes_file, 'w') as out:
+        json.dump(dict(n_source_nodes=source_G.number_of_nodes(),
+                       n_target_nodes=target_G.number_of_nodes(),
+                       runtimes=res['runtimes'], total_time=total_time), out, indent=2)
+    log.info('MUNK embedding complete!')
+
+
+if __name__ == '__main__':
+    run(build_parser().parse_args())

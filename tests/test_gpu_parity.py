@@ -1,0 +1,246 @@
+"""Parity of the CUDA path (through the C ABI, via the munk_b200 API) with the CPU oracle and
+the golden vectors minted from the unmodified reference.
+
+Tolerances: integer/index outputs exact; the Laplacian assembly bit-exact; FP64 results within
+TOL = 1e-8 of max|reference| (the north-star bound) — in practice ~1e-13.  Embeddings are
+compared after orthogonal Procrustes alignment (the RKHS factor is unique only up to a right
+orthogonal factor; scores are invariant)."""
+import numpy as np
+import pytest
+
+from conftest import graph_from_golden, pairs
+from oracle import munk_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-8          # north_star: max-abs error <= 1e-8 relative to max|score|
+TIGHT = 1e-11       # what the FP64 kernels actually deliver on these well-conditioned problems
+
+
+@pytest.fixture(scope="module")
+def m():
+    import munk_b200
+    return munk_b200
+
+
+def homs_of(g):
+    return [tuple(str(x) for x in h) for h in g["homologs"]]
+
+
+# ---------------------------------------------------------------- golden vectors (reference)
+def test_regularized_laplacian_golden(m, golden):
+    for which, key in (("source", "D1"), ("target", "D2")):
+        G = graph_from_golden(golden, which)
+        nodes = [str(x) for x in golden[which + "_nodes"]]
+        D = m.regularized_laplacian(G, nodes, float(golden["lam"]))
+        assert D.shape == golden[key].shape and D.dtype == np.float64 and D.flags.c_contiguous
+        assert oracle.rel_max_err(D, golden[key]) < TIGHT
+        assert np.array_equal(D, D.T)
+
+
+def test_rkhs_factor_golden(m, golden):
+    C = m.rkhs_factor(golden["D1"])
+    assert oracle.rel_max_err(C @ C.T, golden["D1"]) < TIGHT
+    assert np.array_equal(C, np.tril(C))
+    assert oracle.procrustes_residual(C, golden["C1"])[0] < 1e-9
+
+
+def test_embed_matrices_golden(m, golden):
+    C1, D2 = golden["C1"], golden["D2"]
+    src, C2 = m.embed_matrices(C1, D2, pairs(golden["landmark_idxs"]))
+    assert src is C1                                              # munk.py:112 returns the same object
+    assert C2.shape == golden["C2"].shape and C2.flags.f_contiguous
+    assert oracle.rel_max_err(C2, golden["C2"]) < TOL
+    S = m.scores(C1, C2)
+    assert oracle.rel_max_err(S, golden["S"]) < TOL
+    assert oracle.rel_max_err(S, golden["S"]) < 1e-10
+
+
+def test_embed_networks_golden(m, golden):
+    G1, G2 = graph_from_golden(golden, "source"), graph_from_golden(golden, "target")
+    homs, k = homs_of(golden), int(golden["n_landmarks"])
+    (C1, s_nodes), (C2, t_nodes), l_idx, h_idx = m.embed_networks(G1, G2, homs, k, return_idxs=True)
+    assert s_nodes == [str(x) for x in golden["source_nodes"]]
+    assert t_nodes == [str(x) for x in golden["target_nodes"]]
+    assert l_idx == pairs(golden["landmark_idxs"]) and h_idx == pairs(golden["homolog_idxs"])
+    S = m.scores(C1, C2)
+    assert oracle.rel_max_err(S, golden["S"]) < TOL
+    assert oracle.rel_max_err(S, golden["S"]) < 1e-10
+    r1, r2 = oracle.procrustes_residual(C1, golden["C1"], (C2, golden["C2"]))
+    assert r1 < 1e-9 and r2 < 1e-9
+    (_, _), (_, _), l_homs, runtimes = m.embed_networks(G1, G2, homs, k)
+    assert [list(h) for h in l_homs] == [list(h) for h in golden["landmark_homs"]]
+    assert sorted(runtimes) == [str(x) for x in golden["runtime_keys"]]
+    assert all(isinstance(v, float) and v >= 0 for v in runtimes.values())
+
+
+def test_separate_scores_golden(m, golden):
+    import torch
+    got = m.separate_scores(golden["S"], pairs(golden["landmark_idxs"]), pairs(golden["homolog_idxs"]))
+    keys = ("sep_LL_diag", "sep_LL_off", "sep_L_nonL", "sep_HH", "sep_other")
+    for g, key in zip(got, keys):
+        assert np.array_equal(g, golden[key]), key               # selections are bit-exact copies
+    dev_S = torch.from_numpy(golden["S"]).cuda()
+    for g, key in zip(m.separate_scores(dev_S, pairs(golden["landmark_idxs"]), pairs(golden["homolog_idxs"])), keys):
+        assert np.array_equal(g, golden[key]), key
+
+
+# ---------------------------------------------------------------- oracle on seeded inputs
+def test_assembly_bit_exact(m):
+    """A = I + lam L equals numpy's np.eye + lam*L bit for bit, including the degrees (13, 14, 18
+    at lam=0.05) where a fused multiply-add would be 1 ulp off."""
+    import networkx as nx
+    from munk_b200 import util
+    from munk_b200.device import default_device
+    dev = default_device()
+    for n, mm, lam in ((50, 13, 0.05), (777, 5, 0.05), (1000, 14, 0.05), (401, 18, 0.3)):
+        G = nx.barabasi_albert_graph(n, mm, seed=n)
+        nodes = list(range(n))
+        u, v = util.edge_index_arrays(G, nodes)
+        A = dev.assemble(n, u, v, lam)
+        ref = oracle.reglap_matrix(n, oracle.edge_index_arrays(G, nodes), lam)
+        got = A.cpu().numpy()
+        assert np.array_equal(got[:, :n], ref)
+        assert not got[:, n:].any()
+
+
+@pytest.fixture(scope="module")
+def c1_case():
+    from munk_b200 import synthetic
+    n1, n2, mm, H, k = synthetic.CONFIGS["C1"]
+    G1, G2, homs = synthetic.make_case(n1, n2, mm, H)
+    G1, G2 = oracle.simple_two_core(G1), oracle.simple_two_core(G2)
+    assert G1.number_of_nodes() == n1 and G2.number_of_nodes() == n2
+    ref = oracle.embed_networks(G1, G2, homs, k)
+    ref["S"] = oracle.scores(ref["C1"], ref["C2"])
+    return G1, G2, homs, k, ref
+
+
+def test_c1_pipeline_vs_oracle(m, c1_case):
+    """BASELINE config 1: 2000 / 1500 nodes, 300 homologs, 100 landmarks."""
+    G1, G2, homs, k, ref = c1_case
+    (C1, s_nodes), (C2, t_nodes), l_idx, h_idx = m.embed_networks(G1, G2, homs, k, return_idxs=True)
+    assert (s_nodes, t_nodes, l_idx, h_idx) == (ref["source_nodes"], ref["target_nodes"],
+                                                 ref["landmark_idxs"], ref["homolog_idxs"])
+    S = m.scores(C1, C2)
+    err = oracle.rel_max_err(S, ref["S"])
+    assert err < TOL and err < 1e-11, err
+    assert np.array_equal(C1, np.triu(C1))
+    assert oracle.rel_max_err(C1 @ C1.T, ref["D1"]) < TIGHT
+    r1, r2 = oracle.procrustes_residual(C1, ref["C1"], (C2, ref["C2"]))
+    assert r1 < 1e-9 and r2 < 1e-9, (r1, r2)
+    # separate_scores on the GPU result vs the oracle on the same matrix: exact
+    for g, r in zip(m.separate_scores(S, l_idx, h_idx), oracle.separate_scores(S, l_idx, h_idx)):
+        assert np.array_equal(g, r)
+
+
+def test_c1_device_pipeline_and_means(m, c1_case):
+    """Device-resident path (what the CLI and the permutation test use) + the fused means."""
+    from munk_b200 import pipeline
+    from munk_b200.scores_plan import plan_separate_scores
+    G1, G2, homs, k, ref = c1_case
+    res = pipeline.embed_and_score(G1, G2, homs, k)
+    assert oracle.rel_max_err(res["scores"], ref["S"]) < 1e-11
+    assert [tuple(x) for x in res["landmarks"]] == [tuple(x) for x in ref["landmark_homs"]]
+    assert sorted(res["runtimes"]) == ["embed_runtime", "source_regularized_laplacian_runtime",
+                                       "source_rkhs_factorization_runtime",
+                                       "target_regularized_laplacian_runtime"]
+    inp = pipeline.graph_inputs(G1, G2, homs, k)
+    emb = pipeline.embed_device(len(ref["source_nodes"]), inp["edges1"], len(ref["target_nodes"]),
+                                inp["edges2"], inp["landmark_idxs"])
+    plan = plan_separate_scores(emb.n1, emb.n2, ref["landmark_idxs"], ref["homolog_idxs"])
+    out = plan.means(emb.dev, emb.scores()).cpu().numpy()
+    diff, other_mean, hom_mean = oracle.difference_in_means(ref["C1"], ref["D2"], ref["homolog_idxs"], k)
+    assert abs(out[0] - hom_mean) <= 1e-10 * abs(hom_mean)
+    assert abs(out[1] - other_mean) <= 1e-10 * abs(other_mean)
+    assert abs(out[2] - diff) <= 1e-10 * abs(diff)
+    assert out[3] == len(ref["homolog_idxs"]) - k
+
+
+def test_one_to_many_homologs_match_pinv(m):
+    """A source landmark listed twice makes C1[Ls,:] rank deficient: np.linalg.pinv returns the
+    rank-(k-1) least-squares answer and so must we."""
+    from munk_b200 import synthetic
+    G1, G2, homs = synthetic.make_case(300, 260, 4, 60, seeds=(7, 8))
+    homs = homs[:9] + [(homs[2][0], homs[30][1]), (homs[2][0], homs[31][1])] + homs[9:]
+    k = 20
+    ref = oracle.embed_networks(G1, G2, homs, k)
+    (C1, _), (C2, _), l_idx, _ = m.embed_networks(G1, G2, homs, k, return_idxs=True)
+    assert l_idx == ref["landmark_idxs"] and len({s for s, _ in l_idx}) == k - 2
+    assert oracle.rel_max_err(m.scores(C1, C2), oracle.scores(ref["C1"], ref["C2"])) < 1e-10
+
+
+@pytest.mark.parametrize("n1,n2,mm,H,k", [(3, 4, 2, 3, 2), (130, 100, 3, 30, 30), (257, 513, 2, 40, 1),
+                                          (777, 301, 5, 100, 64)])
+def test_ragged_sizes(m, n1, n2, mm, H, k):
+    """Orders that are tiny, odd, or straddle the 128-wide tile / leaf boundaries."""
+    import networkx as nx
+    if n1 == 3:
+        G1 = nx.relabel_nodes(nx.complete_graph(3), {i: "s%d" % i for i in range(3)})
+        G2 = nx.relabel_nodes(nx.cycle_graph(4), {i: "t%d" % i for i in range(4)})
+        homs = [("s0", "t1"), ("s2", "t0"), ("s1", "t3")]
+    else:
+        from munk_b200 import synthetic
+        G1, G2, homs = synthetic.make_case(n1, n2, mm, H, seeds=(n1, n2), padded=False)
+    ref = oracle.embed_networks(G1, G2, homs, k)
+    (C1, s_nodes), (C2, _), l_idx, h_idx = m.embed_networks(G1, G2, homs, k, return_idxs=True)
+    assert s_nodes == ref["source_nodes"] and l_idx == ref["landmark_idxs"] and h_idx == ref["homolog_idxs"]
+    assert oracle.rel_max_err(m.scores(C1, C2), oracle.scores(ref["C1"], ref["C2"])) < 1e-10
+    D2 = m.regularized_laplacian(G2, ref["target_nodes"], 0.05)
+    assert oracle.rel_max_err(D2, ref["D2"]) < TIGHT
+
+
+def test_error_behaviour(m):
+    import networkx as nx
+    G = nx.relabel_nodes(nx.complete_graph(5), str)
+    with pytest.raises(AssertionError):                       # munk.py:129
+        m.embed_networks(G, G, [("0", "1")], 2)
+    with pytest.raises(KeyError):                             # munk.py:153 (unfiltered homolog)
+        m.embed_networks(G, G, [("0", "nope")], 1)
+    with pytest.raises(np.linalg.LinAlgError):
+        m.rkhs_factor(-np.eye(200))
+    assert m.regularized_laplacian(G, [], 0.05).shape == (0, 0)
+
+
+def test_scores_layouts(m):
+    rng = np.random.default_rng(5)
+    X1, X2 = rng.standard_normal((300, 129)), rng.standard_normal((171, 129))
+    ref = X1 @ X2.T
+    assert oracle.rel_max_err(m.scores(X1, X2), ref) < 1e-13
+    assert oracle.rel_max_err(m.scores(X1, np.asfortranarray(X2)), ref) < 1e-13
+
+
+# ---------------------------------------------------------------- full size, by properties
+def test_c3_full_size_properties(m):
+    """BASELINE config 3 (20000 / 16000 nodes, 4000 homologs, 400 landmarks).  The oracle needs
+    ~8 minutes there, so parity is checked through size-independent properties:
+    D 1 = 1, S[Ls,:] = D2[Lt,:] (interpolation), S = D1[:,Ls] D1[Ls,Ls]^-1 D2[Lt,:] on sampled
+    columns, exact integer outputs, and an fp64 residual check of the factor on sampled rows."""
+    import torch
+    from munk_b200 import pipeline, synthetic
+    n1, n2, mm, H, k = synthetic.CONFIGS["C3"]
+    G1, G2, homs = synthetic.make_case(n1, n2, mm, H)
+    inp = pipeline.graph_inputs(G1, G2, homs, k)
+    assert len(inp["source_nodes"]) == n1 and len(inp["target_nodes"]) == n2
+    emb = pipeline.embed_device(n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"])
+    W1, W2, P = emb.W1[:, :n1], emb.W2[:, :n2], emb.P[:, :n2]
+    S = emb.scores()[:, :n2]
+    ones1 = torch.ones(n1, dtype=torch.float64, device=W1.device)
+    L1 = torch.tril(W1)
+    assert float((L1.t() @ (L1 @ ones1) - 1).abs().max()) < 1e-12        # D1 1 = 1
+    ls = torch.tensor([a for a, _ in inp["landmark_idxs"]], device=W1.device)
+    lt = torch.tensor([b for _, b in inp["landmark_idxs"]], device=W1.device)
+    L2 = torch.tril(W2)
+    D2_rows = L2[:, lt].t() @ L2                                          # D2[Lt,:]
+    assert float((S[ls, :] - D2_rows).abs().max() / D2_rows.abs().max()) < 1e-11
+    # residual of the source factor on sampled rows: rows of (W1 A1) must be unit vectors
+    A1 = emb.dev.assemble(n1, inp["edges1"][0], inp["edges1"][1], 0.05)[:, :n1]
+    rows = torch.arange(0, n1, 997, device=W1.device)
+    R = (L1[rows, :] @ A1) @ L1.t()                                       # = I[rows, :]
+    E = torch.zeros_like(R); E[torch.arange(len(rows)), rows] = 1
+    assert float((R - E).abs().max()) < 1e-11
+    # rank-k identity on sampled target columns
+    cols = torch.arange(0, n2, 1601, device=W1.device)
+    D1_Ls = L1.t() @ L1[:, ls]                                            # D1[:, Ls]
+    S_ref = D1_Ls @ torch.linalg.solve(D1_Ls[ls, :], D2_rows[:, cols])
+    assert float((S[:, cols] - S_ref).abs().max() / S_ref.abs().max()) < 1e-10
+    assert float(S.min()) > 0                                             # inverse M-matrix: scores > 0

@@ -1,0 +1,132 @@
+"""Host-side logic of munk_b200 (no GPU): node/homolog index mapping must be bit-exact with the
+reference, the separate_scores plan must reproduce the reference's mask order, file formats."""
+import re
+
+import networkx as nx
+import numpy as np
+import pytest
+
+from conftest import graph_from_golden, pairs
+from oracle import munk_oracle as oracle
+
+
+def test_util_matches_oracle_and_reference_indices(golden):
+    from munk_b200 import util
+    from munk_b200.pipeline import graph_inputs
+    G1, G2 = graph_from_golden(golden, "source"), graph_from_golden(golden, "target")
+    homs = [tuple(str(x) for x in h) for h in golden["homologs"]]
+    assert util.sorted_nodes(G1) == [str(x) for x in golden["source_nodes"]]
+    assert util.node_to_index(G2) == oracle.node_to_index(G2)
+    assert util.index_to_node(G2) == oracle.index_to_node(G2)
+    assert util.node_to_index(["b", "a"], dtype="list") == {"b": 0, "a": 1}
+    with pytest.raises(NotImplementedError):
+        util.node_to_index(G1, dtype="nope")
+    assert util.homologs_in_graphs(G1, G2, homs + [("zz", "yy")]) == homs
+    inp = graph_inputs(G1, G2, homs, int(golden["n_landmarks"]))
+    assert inp["landmark_idxs"] == pairs(golden["landmark_idxs"])
+    assert [list(h) for h in inp["landmark_homs"]] == [list(h) for h in golden["landmark_homs"]]
+    # edge arrays describe the same undirected edge set as the oracle's
+    def canon(u, v):
+        e = np.stack([np.minimum(u, v), np.maximum(u, v)], axis=1)
+        return np.unique(e, axis=0)
+    assert np.array_equal(canon(*inp["edges1"]), golden["source_edges"])
+    assert np.array_equal(canon(*inp["edges2"]), golden["target_edges"])
+    with pytest.raises(AssertionError):
+        graph_inputs(G1, G2, homs, len(homs) + 1)        # munk.py:129
+
+
+def test_two_core_and_simplify_match_oracle():
+    from munk_b200 import util
+    G = nx.barabasi_albert_graph(120, 2, seed=4)          # loses a node in the 2-core
+    G.add_edge(5, 5)
+    G.add_edges_from([(1000, 1001), (1001, 1002), (1002, 1000)])   # second component
+    a = util.simple_two_core(G.copy(), verbose=False)
+    b = oracle.simple_two_core(G.copy())
+    assert sorted(a.nodes()) == sorted(b.nodes()) and sorted(map(sorted, a.edges())) == sorted(map(sorted, b.edges()))
+    assert a.number_of_nodes() < 120 and 1000 not in a and not list(nx.selfloop_edges(a))
+    assert min(d for _, d in a.degree()) >= 2
+
+
+def test_edge_index_arrays_rules():
+    from munk_b200 import util
+    G = nx.Graph([("a", "b"), ("b", "c"), ("c", "c"), ("c", "d")])
+    u, v = util.edge_index_arrays(G, ["c", "a", "b"])     # subset + custom order, self loop dropped
+    assert sorted(zip(u.tolist(), v.tolist())) in ([(1, 2), (2, 0)], [(0, 2), (1, 2)], [(1, 2), (0, 2)], [(2, 0), (1, 2)]) \
+        or sorted(map(sorted, zip(u.tolist(), v.tolist()))) == [[0, 2], [1, 2]]
+    assert u.dtype == np.int32
+    G["a"]["b"]["weight"] = 2.5
+    with pytest.raises(NotImplementedError):
+        util.edge_index_arrays(G, ["a", "b"])
+
+
+def test_file_formats_roundtrip(tmp_path):
+    from munk_b200 import synthetic, util
+    G1, G2, homs = synthetic.make_case(60, 50, 3, 20, seeds=(5, 6))
+    synthetic.write_edgelist(G1, tmp_path / "s.txt", extras=True)
+    synthetic.write_homologs(homs, tmp_path / "h.tsv")
+    R = nx.read_edgelist(tmp_path / "s.txt", encoding="ascii")
+    R = util.simple_two_core(R, verbose=False)
+    assert sorted(R.nodes()) == sorted(G1.nodes()) and R.number_of_edges() == G1.number_of_edges()
+    assert util.read_homolog_list(tmp_path / "h.tsv") == homs
+
+
+def emulate_plan(plan, S):
+    """numpy re-statement of separate_scores_kernel's placement rule (munk_b200/csrc/scores.cu)."""
+    o_lloff = np.full(plan.n_lloff, np.nan); o_lnonl = np.full(plan.n_lnonl, np.nan)
+    o_other = np.full(plan.n_other, np.nan)
+    for i in range(plan.n1):
+        pc = plan.p_col[plan.p_ptr[i]:plan.p_ptr[i + 1]]
+        hc = plan.h_col[plan.h_ptr[i]:plan.h_ptr[i + 1]]
+        for j in range(plan.n2):
+            rk = plan.colrank[j]
+            if plan.rowL[i]:
+                if plan.colL[j]:
+                    if j not in pc:
+                        o_lloff[plan.off_lloff[i] + rk - np.sum(pc < j)] = S[i, j]
+                else:
+                    o_lnonl[plan.off_lnonl[i] + j - rk] = S[i, j]
+            elif plan.colL[j]:
+                o_lnonl[plan.off_lnonl[i] + rk] = S[i, j]
+            elif j not in hc:
+                before = sum(1 for c in hc if c < j and not plan.colL[c])
+                o_other[plan.off_other[i] + (j - rk) - before] = S[i, j]
+    hh = S[plan.h_row, plan.h_col]
+    return S[plan.ls, plan.lt], o_lloff, o_lnonl, hh, o_other
+
+
+def test_separate_scores_plan_reproduces_reference_order(golden):
+    from munk_b200.scores_plan import plan_separate_scores
+    S = golden["S"]
+    plan = plan_separate_scores(S.shape[0], S.shape[1], pairs(golden["landmark_idxs"]), pairs(golden["homolog_idxs"]))
+    got = emulate_plan(plan, S)
+    for g, key in zip(got, ("sep_LL_diag", "sep_LL_off", "sep_L_nonL", "sep_HH", "sep_other")):
+        assert np.array_equal(g, golden[key]), key
+
+
+def test_separate_scores_plan_edge_cases():
+    from munk_b200.scores_plan import plan_separate_scores
+    rng = np.random.default_rng(0)
+    S = rng.standard_normal((9, 7))
+    # repeated landmark rows/cols, homolog cells inside landmark rows/cols, duplicate homologs
+    lidx = [(1, 2), (1, 5), (4, 2), (8, 6)]
+    hidx = lidx + [(0, 0), (0, 3), (0, 0), (1, 1), (3, 2), (7, 6), (5, 4)]
+    plan = plan_separate_scores(9, 7, lidx, hidx)
+    ref = oracle.separate_scores(S, lidx, hidx)
+    for g, r in zip(emulate_plan(plan, S), ref):
+        assert np.array_equal(g, r)
+    with pytest.raises(IndexError):
+        plan_separate_scores(9, 7, [(9, 0)], hidx)
+
+
+def test_cli_flag_surface_matches_reference():
+    """Same flags and defaults as scripts/compute_embeddings.py:17-31 of the reference."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "compute_embeddings.py")
+    src = open(path).read()
+    for flag in ("-se", "--source_edgelist", "-te", "--target_edgelist", "-hf", "--homolog_list", "-so",
+                 "--source_output_file", "-to", "--target_output_file", "-sim", "--sim_scores_output_file",
+                 "-lo", "--landmarks_output_file", "-r", "--runtimes_file", "-n", "--n_landmarks", "-rs",
+                 "--random_seed", "--src_lam", "--tgt_lam"):
+        assert re.search(r"'%s'" % re.escape(flag), src), flag
+    assert "default=400" in src and "default=28791" in src and src.count("default=0.05") == 2
