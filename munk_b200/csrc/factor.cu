@@ -16,102 +16,16 @@
 // into a copy.
 #include "dgemm.cuh"
 #include "factor.cuh"
+#include "leaf.cuh"
 #include "workspace.cuh"
+
+#include <algorithm>
 
 namespace munk {
 
 namespace {
 
 constexpr int LEAF = MUNK_LEAF;
-constexpr int LDS_ = LEAF + 1;          // padded shared row: L in the lower part, X^T above it
-constexpr int LEAF_THREADS = 512;
-
-// Cholesky + inverse of one nb x nb (nb <= 128) diagonal block.
-//   A     : in: symmetric block (lower part read); out: L in the lower part, zeros above
-//   Linv  : out: L^-1 (row-major, ld = 128, lower; zeros above and in the unused tail)
-//   info  : set to (gidx + j + 1) by atomicMin-like rule if pivot j is not positive
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
-potrf_leaf_kernel(double* __restrict__ A, long lda, int nb, double* __restrict__ Linv, int gidx,
-                  int* __restrict__ info) {
-  extern __shared__ double sm[];      // [LEAF][LDS_]
-  __shared__ int bad;
-  __shared__ double rdiag[LEAF];      // 1 / L[i][i]
-  const int tid = threadIdx.x;
-  if (tid == 0) bad = 0;
-
-  // load the lower triangle (coalesced along rows)
-  for (int idx = tid; idx < nb * LEAF; idx += LEAF_THREADS) {
-    const int r = idx / LEAF, c = idx % LEAF;
-    if (c < nb) sm[r * LDS_ + c] = (c <= r) ? A[(long)r * lda + c] : 0.0;
-  }
-  __syncthreads();
-
-  // right-looking unblocked Cholesky in shared memory
-  for (int j = 0; j < nb; ++j) {
-    const double d = sm[j * LDS_ + j];
-    if (!(d > 0.0)) {                 // also catches NaN
-      if (tid == 0) bad = j + 1;
-      break;                          // uniform: every thread reads the same d
-    }
-    const double s = sqrt(d);
-    __syncthreads();                  // everyone has read d before it is overwritten
-    for (int i = j + tid; i < nb; i += LEAF_THREADS)
-      sm[i * LDS_ + j] = (i == j) ? s : sm[i * LDS_ + j] / s;
-    __syncthreads();
-    // trailing update of the lower triangle: rows i > j, columns j < k <= i
-    const int rem = nb - j - 1;
-    for (int idx = tid; idx < rem * rem; idx += LEAF_THREADS) {
-      const int i = j + 1 + idx / rem, k = j + 1 + idx % rem;
-      if (k <= i) sm[i * LDS_ + k] -= sm[i * LDS_ + j] * sm[k * LDS_ + j];
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  if (bad) {
-    if (tid == 0) atomicCAS(info, 0, gidx + bad);   // keep the first failure
-    return;
-  }
-
-  for (int i = tid; i < nb; i += LEAF_THREADS) rdiag[i] = 1.0 / sm[i * LDS_ + i];
-  __syncthreads();
-
-  // Inverse X = L^-1, column by column: 4 lanes share column c, lane q takes k = c+q, c+q+4, ..
-  // x[k] of column c lives at sm[c][k+1] (the unused upper part), so no second array is needed.
-  {
-    const int q = tid & 3;
-    for (int c = tid >> 2; c < nb; c += LEAF_THREADS / 4) {
-      // (the 4 lanes of a column are in one warp; all loop bounds are uniform across them)
-      double* x = sm + c * LDS_ + 1;              // x[k] for k >= c
-      if (q == 0) x[c] = rdiag[c];
-      __syncwarp(0xfu << (threadIdx.x & 28));
-      for (int i = c + 1; i < nb; ++i) {
-        double acc = 0.0, acc2 = 0.0;
-        int k = c + q;
-        for (; k + 4 < i; k += 8) {
-          acc += sm[i * LDS_ + k] * x[k];
-          acc2 += sm[i * LDS_ + k + 4] * x[k + 4];
-        }
-        if (k < i) acc += sm[i * LDS_ + k] * x[k];
-        acc += acc2;
-        acc += __shfl_xor_sync(0xfu << (threadIdx.x & 28), acc, 1, 4);
-        acc += __shfl_xor_sync(0xfu << (threadIdx.x & 28), acc, 2, 4);
-        if (q == 0) x[i] = -acc * rdiag[i];
-        __syncwarp(0xfu << (threadIdx.x & 28));
-      }
-    }
-  }
-  __syncthreads();
-
-  // write back L (zero strict upper) and X (row-major lower, zero elsewhere up to 128 x 128)
-  for (int idx = tid; idx < nb * LEAF; idx += LEAF_THREADS) {
-    const int r = idx / LEAF, c = idx % LEAF;
-    if (c < nb) A[(long)r * lda + c] = (c <= r) ? sm[r * LDS_ + c] : 0.0;
-  }
-  for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
-    const int r = idx / LEAF, c = idx % LEAF;
-    Linv[idx] = (r < nb && c <= r) ? sm[c * LDS_ + r + 1] : 0.0;
-  }
-}
 
 // dst (nb x nb block inside a row-major matrix) <- src (128-ld leaf inverse)
 __global__ void copy_leaf_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ src,
@@ -136,15 +50,8 @@ struct Rec {
 };
 
 int leaf_potrf(Rec& r, double* A, long ld, int nb, int gidx) {
-  static bool configured = false;
-  const int smem = LEAF * LDS_ * 8;
-  if (!configured) {
-    MUNK_CUDA_TRY(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  potrf_leaf_kernel<<<1, LEAF_THREADS, smem, r.stream>>>(A, ld, nb, r.linv + (long)(gidx / LEAF) * LEAF * LEAF,
-                                                         gidx, r.ws->info);
-  MUNK_CUDA_TRY(cudaGetLastError());
+  MUNK_TRY(launch_potrf_leaf(A, ld, nb, r.linv + (long)(gidx / LEAF) * LEAF * LEAF, gidx, r.ws->info,
+                             r.stream));
   r.ws->launches++;
   r.ws->flops += (double)nb * nb * nb / 3.0;
   return MUNK_OK;

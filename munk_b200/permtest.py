@@ -1,0 +1,234 @@
+"""Homology-scores permutation test on B200s
+(reference: experiments/homology-scores-permutation-test/permtest.py, gen_random_network.py).
+
+The per-permutation unit is the reference's `difference_in_means` (permtest.py:68-80):
+embed_matrices + S = C1 @ C2hat.T + separate_scores + mean(H_H) - mean(other).  Two kinds of
+permutation are supported ("C4 semantics"):
+
+  "indices" (BASELINE.json config 4): the graphs, hence the factors W1, W2, stay fixed and
+      permutation p shuffles the homolog list with np.random.default_rng(1000 + p) before the
+      first n_landmarks pairs are taken as landmarks;
+  "graphs"  (the reference's own experiment): every permutation draws a degree-preserving random
+      graph pair (gen_random_network.py:50-84), factors it on the GPU, and keeps the homolog list.
+
+Permutations are independent units: rank r of `world` takes p = r, r + world, ... with no
+data-path collective; one all-gather of 3 doubles per permutation at the end.
+"""
+import numpy as np
+import torch
+
+from . import util
+from .device import default_device, landmark_groups
+from .pipeline import graph_inputs
+from .scores_plan import plan_separate_scores
+
+
+# ------------------------------------------------------------------ statistics (host scalars)
+def one_tail_pval(observed, permuted):
+    """permtest.py:101-104: (#permuted > observed) / N, the count, N."""
+    permuted = np.asarray(permuted)
+    n_significant = float(np.sum(permuted > observed))
+    return n_significant / float(len(permuted)), n_significant, float(len(permuted))
+
+
+def effect_size(observed, control):
+    """permtest.py:106-109: z-score with the population standard deviation."""
+    return (observed - np.mean(control)) / np.std(control)
+
+
+# ------------------------------------------------------------------ the unit, host-array API
+def munk_embed_wrapper(source_data, target_data, homologs, n_landmarks, ref_source_nodes,
+                       ref_target_nodes):
+    """permtest.py:37-56 — host dicts in (source_data['C'], target_data['D'], node lists),
+    (sim_scores, landmark_idxs, homolog_idxs) out."""
+    from .munk import embed_matrices, scores
+    source_nodes, target_nodes = source_data['nodes'], target_data['nodes']
+    assert source_nodes == ref_source_nodes
+    assert target_nodes == ref_target_nodes
+    s_pos = {n: i for i, n in enumerate(source_nodes)}
+    t_pos = {n: i for i, n in enumerate(target_nodes)}
+    homolog_idxs = [(s_pos[a], t_pos[b]) for a, b in homologs]
+    landmark_idxs = homolog_idxs[:n_landmarks]
+    source_C, target_C_hat = embed_matrices(source_data['C'], target_data['D'], landmark_idxs)
+    return scores(source_C, target_C_hat), landmark_idxs, homolog_idxs
+
+
+def dissim_diff(sim_scores, landmark_idxs, homolog_idxs):
+    """permtest.py:58-66 — (hom_mean - other_mean, other_mean, hom_mean), computed on the device
+    without materialising the five selections."""
+    dev = default_device()
+    S = sim_scores if torch.is_tensor(sim_scores) else \
+        torch.from_numpy(np.ascontiguousarray(sim_scores, dtype=np.float64)).to(dev.torch_device)
+    plan = plan_separate_scores(S.shape[0], S.shape[1], landmark_idxs, homolog_idxs)
+    hom_mean, other_mean, diff = plan.means(dev, S).cpu().numpy()[:3]
+    return float(diff), float(other_mean), float(hom_mean)
+
+
+def difference_in_means(source_data, target_data, homologs, n_landmarks, ref_source_nodes,
+                        ref_target_nodes):
+    """permtest.py:68-80."""
+    return dissim_diff(*munk_embed_wrapper(source_data, target_data, homologs, n_landmarks,
+                                           ref_source_nodes, ref_target_nodes))
+
+
+# ------------------------------------------------------------------ the unit, device resident
+class FactoredPair:
+    """W1, W2 (inverse Cholesky factors of I + lam L) of one graph pair, on the device."""
+
+    def __init__(self, dev, n1, edges1, n2, edges2, lam=0.05):
+        self.dev, self.n1, self.n2 = dev, n1, n2
+        self.W1 = dev.kernel_factor(n1, edges1[0], edges1[1], lam)
+        self.W2 = dev.kernel_factor(n2, edges2[0], edges2[1], lam)
+        self._S = None
+
+    def statistic(self, homolog_idxs, n_landmarks):
+        """CUDA tensor {hom_mean, other_mean, diff, |H_H|, |other|}; nothing is synchronised."""
+        dev = self.dev
+        landmark_idxs = homolog_idxs[:n_landmarks]
+        uniq, gptr, members = landmark_groups([int(a) for a, _ in landmark_idxs])
+        Q1 = dev.gather_cols_lower(self.W1, self.n1, uniq)
+        B = dev.target_landmark_rows(self.W2, self.n2, [int(b) for _, b in landmark_idxs])
+        P = dev.project(Q1, self.n1, B, self.n2, (gptr, members))
+        if self._S is None:
+            self._S = dev.empty(self.n1, self.n2)
+        S = dev.score(self.W1, self.n1, P, self.n2, out=self._S)
+        plan = plan_separate_scores(self.n1, self.n2, landmark_idxs, homolog_idxs)
+        return plan.means(dev, S)
+
+
+def permuted_homolog_idxs(homolog_idxs, p):
+    """Permutation p of the 'indices' mode: seeded shuffle of the homolog index pairs."""
+    order = np.random.default_rng(1000 + p).permutation(len(homolog_idxs))
+    return [homolog_idxs[i] for i in order]
+
+
+# ------------------------------------------------------------------ random graphs (mode "graphs")
+def perturbed_graph(seed_graph, rng):
+    """Degree-preserving random graph on the same node names (gen_random_network.py:50-65):
+    configuration model on a shuffled degree sequence, nodes renamed so that every name keeps
+    its degree, parallel edges and self loops dropped, then the simple 2-core.  Unlike the
+    reference (unseeded np.random.shuffle) the generator is passed in, so runs are repeatable."""
+    import networkx as nx
+    names_degs = list(seed_graph.degree)
+    order = rng.permutation(len(names_degs))
+    names_degs = [names_degs[i] for i in order]
+    new_G = nx.configuration_model([d for _, d in names_degs], seed=int(rng.integers(2 ** 31)))
+    by_deg_new, by_deg_old = {}, {}
+    for name, d in names_degs:
+        by_deg_new.setdefault(d, []).append(name)
+    for node, d in new_G.degree:
+        by_deg_old.setdefault(d, []).append(node)
+    mapping = {}
+    for d, new_names in by_deg_new.items():
+        shuffled = [new_names[i] for i in rng.permutation(len(new_names))]
+        mapping.update(zip(by_deg_old[d], shuffled))
+    return util.simple_two_core(nx.Graph(nx.relabel_nodes(new_G, mapping)), verbose=False)
+
+
+def safe_perturbed_graph(seed_graph, rng, n_tries=10):
+    """gen_random_network.py:67-73 — retry until the 2-core keeps every node of the seed."""
+    for attempt in range(n_tries):
+        G = perturbed_graph(seed_graph, rng)
+        if not (set(G.nodes) ^ set(seed_graph.nodes)):
+            return G, attempt + 1
+    raise Exception('no random graph kept all nodes in %d tries' % n_tries)
+
+
+def gen_random_network_data(seed_graph, n_tries=10, rng=None, lam=0.05, host=True):
+    """gen_random_network.py:78-84 — dict(G, D, C, nodes) of one random graph (lam fixed at 0.05
+    in the reference).  With host=False D and C are replaced by the device factor W."""
+    rng = rng or np.random.default_rng()
+    G, tries = safe_perturbed_graph(seed_graph, rng, n_tries)
+    nodes = sorted(G.nodes())
+    dev = default_device()
+    u, v = util.edge_index_arrays(G, nodes)
+    n = len(nodes)
+    W = dev.kernel_factor(n, u, v, lam)
+    if not host:
+        return dict(G=G, W=W, nodes=nodes), tries
+    D = dev.download(dev.gram_lower(W, n, ld=n + (n & 1)), n, n)
+    C = dev.download(dev.transpose_lower(W, n, ld=n + (n & 1)), n, n)
+    return dict(G=G, D=D, C=C, nodes=nodes), tries
+
+
+# ------------------------------------------------------------------ sharding + gather
+def shard(n_units, rank, world):
+    """Units of this rank: rank, rank + world, ... (round-robin)."""
+    return list(range(rank, n_units, world))
+
+
+def gather_results(local, n_units, rank, world, device=None):
+    """All ranks' (unit -> 3 values) merged into an (n_units, 3) array on every rank.
+
+    One all-gather of a padded (units_per_rank, 3) float64 tensor; works with NCCL (CUDA
+    tensors) and gloo (CPU tensors).  Missing units (errors) are NaN rows."""
+    import torch.distributed as dist
+    per = (n_units + world - 1) // world
+    buf = torch.full((per, 3), float('nan'), dtype=torch.float64)
+    for slot, unit in enumerate(shard(n_units, rank, world)):
+        if unit in local and local[unit] is not None:
+            buf[slot] = torch.as_tensor(local[unit], dtype=torch.float64)
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        parts = [buf]
+    else:
+        if device is not None:
+            buf = buf.to(device)
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf)
+        parts = [p.cpu() for p in parts]
+    out = np.full((n_units, 3), np.nan)
+    for r, part in enumerate(parts):
+        units = shard(n_units, r, world)
+        out[units] = part.numpy()[:len(units)]
+    return out
+
+
+def run_permutation_test(source_G, target_G, homologs, n_landmarks, n_permutations, lam=0.05,
+                         mode="indices", rank=0, world=1, seed=0, n_tries=50):
+    """The whole experiment (permtest.py:111-187) with permutations sharded over `world` ranks.
+
+    Returns dict(pval, effect_size, n_permutations, n_less_than, errs, real, random) on every rank.
+    """
+    dev = default_device()
+    inp = graph_inputs(source_G, target_G, homologs, n_landmarks)
+    s_pos, t_pos = inp["s_pos"], inp["t_pos"]
+    homolog_idxs = [(s_pos[a], t_pos[b]) for a, b in homologs]
+    n1, n2 = len(inp["source_nodes"]), len(inp["target_nodes"])
+    real_pair = FactoredPair(dev, n1, inp["edges1"], n2, inp["edges2"], lam)
+    real = real_pair.statistic(homolog_idxs, n_landmarks).cpu().numpy()
+
+    pending = {}
+    for p in shard(n_permutations, rank, world):
+        try:
+            if mode == "indices":
+                pending[p] = real_pair.statistic(permuted_homolog_idxs(homolog_idxs, p), n_landmarks)
+            elif mode == "graphs":
+                rng = np.random.default_rng([seed, p])
+                G1, _ = safe_perturbed_graph(source_G, rng, n_tries)
+                G2, _ = safe_perturbed_graph(target_G, rng, n_tries)
+                e1 = util.edge_index_arrays(G1, inp["source_nodes"])
+                e2 = util.edge_index_arrays(G2, inp["target_nodes"])
+                pair = FactoredPair(dev, n1, e1, n2, e2, lam)
+                pending[p] = pair.statistic(homolog_idxs, n_landmarks)
+                del pair
+            else:
+                raise ValueError("mode must be 'indices' or 'graphs'")
+        except Exception as exc:     # permtest.py:97-99: count the failure, keep going
+            print('ERROR with permutation {}: {}'.format(p, exc))
+            pending[p] = None
+    torch.cuda.current_stream(dev.index).synchronize()
+    local = {}
+    for p, t in pending.items():
+        if t is None:
+            local[p] = None
+        else:
+            hom_mean, other_mean, diff = t.cpu().numpy()[:3]
+            local[p] = (diff, other_mean, hom_mean)
+    table = gather_results(local, n_permutations, rank, world, device=dev.torch_device)
+    ok = ~np.isnan(table[:, 0])
+    diffs = table[ok, 0]
+    pval, n_less, n_obs = one_tail_pval(real[2], diffs)
+    return dict(pval=pval, effect_size=float(effect_size(real[2], diffs)), n_permutations=n_obs,
+                n_less_than=n_less, errs=int((~ok).sum()),
+                real=dict(mean_diff=float(real[2]), non_hom_mean=float(real[1]), hom_mean=float(real[0])),
+                random=dict(mean_diffs=table[ok, 0], non_hom_means=table[ok, 1], hom_means=table[ok, 2]))
