@@ -36,12 +36,12 @@ UNIT = "TFLOP/s"
 
 
 def pipeline_flops(n1, n2, k):
-    """Useful flops of the build's algorithm: chol n^3/3 + trtri n^3/3 per graph,
-    D2[Lt,:] rows k*n2^2, Gram k^2*n1 (symmetric... counted dense 2*k^2*n1), projection
-    2*n1*n2*k, triangular score product n1^2*n2."""
+    """Useful flops of the build's algorithm (SURVEY 8d): source chol n1^3/3 + trtri n1^3/3;
+    target chol n2^3/3 + the k-column solve 2*n2^2*k for D2[Lt,:] (no full target inverse);
+    Gram 2*k^2*n1, small solves, projection 2*n1*n2*k, triangular score product n1^2*n2."""
     src = 2.0 * n1 ** 3 / 3.0
-    tgt = 2.0 * n2 ** 3 / 3.0
-    rows = 1.0 * k * n2 ** 2
+    tgt = 1.0 * n2 ** 3 / 3.0
+    rows = 2.0 * k * n2 ** 2
     gram = 2.0 * k * k * n1
     solve = 2.0 * k * k * n2 + 2.0 * k ** 3 / 3.0
     proj = 2.0 * n1 * n2 * k
@@ -207,9 +207,8 @@ def run_gpu(args):
         dev.trtri(A1, n1, linv1); mark("trtri_src")
         dev.assemble(n2, edges2[0], edges2[1], 0.05, out=A2); mark("assemble_tgt")
         dev.potrf(A2, n2, linv=linv2, check_info=False); mark("potrf_tgt")
-        dev.trtri(A2, n2, linv2); mark("trtri_tgt")
         Q1 = dev.gather_cols_lower(A1, n1, uniq_idx)
-        B = dev.target_landmark_rows(A2, n2, tgt_idx)
+        B = dev.target_landmark_rows_from_factor(A2, linv2, n2, tgt_idx)
         P = dev.project(Q1, n1, B, n2, (gptr, members)); mark("embed")
         dev.score(A1, n1, P, n2, out=S_buf); mark("score")
         if record:
@@ -305,7 +304,6 @@ def run_gpu(args):
             "trtri_src": {"ms": med["trtri_src"], "tflops": n1 ** 3 / 3 / med["trtri_src"] / 1e9},
             "assemble_tgt": {"ms": med["assemble_tgt"], "GBps": n2 * A2.stride(0) * 8 / med["assemble_tgt"] / 1e6},
             "potrf_tgt": {"ms": med["potrf_tgt"], "tflops": n2 ** 3 / 3 / med["potrf_tgt"] / 1e9},
-            "trtri_tgt": {"ms": med["trtri_tgt"], "tflops": n2 ** 3 / 3 / med["trtri_tgt"] / 1e9},
             "embed": {"ms": med["embed"], "tflops": (fl["rows"] + fl["gram"] + fl["solve"] + fl["proj"]) / med["embed"] / 1e9},
             "score": {"ms": score_ms, "tflops": achieved},
         }

@@ -80,6 +80,18 @@ int munk_potrf_info(munk_workspace_t* ws, int* info_host, void* stream);
  */
 int munk_trtri(munk_workspace_t* ws, int n, double* L, long ld, double* linv, void* stream);
 
+/*
+ * B (n x nrhs, in place) <- L^-1 B (transposed = 0) or L^-T B (transposed = 1) with the factor
+ * left by munk_potrf.  Two calls give A^-1 B; with B = the landmark columns of the identity this
+ * is target_D[:, target_idxs] (munk/munk/munk.py:110) without forming the full inverse.
+ */
+int munk_trsm_left(munk_workspace_t* ws, int n, const double* L, long ld, const double* linv,
+                   int transposed, int nrhs, double* B, long ldb, void* stream);
+
+/* out (cols x rows) = in (rows x cols)^T, row-major. */
+int munk_transpose(int rows, int cols, const double* in, long ldi, double* out, long ldo,
+                   void* stream);
+
 /* D = W^T W, full symmetric n x n (the value np.linalg.inv returns at munk/munk/munk.py:83). */
 int munk_gram_lower(munk_workspace_t* ws, int n, const double* W, long ldw, double* D, long ldd,
                     void* stream);

@@ -27,6 +27,9 @@ SIGNATURES = {
     "munk_potrf_info": (c_int, [c_void_p, _P(c_int), c_void_p]),
     "munk_trtri": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p]),
     "munk_gram_lower": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p]),
+    "munk_trsm_left": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_int, c_int, c_void_p,
+                               c_long, c_void_p]),
+    "munk_transpose": (c_int, [c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p]),
     "munk_dgemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long,
                            c_void_p, c_long, c_double, c_void_p, c_long, c_int, c_void_p]),
     "munk_gather_cols_lower": (c_int, [c_int, c_void_p, c_long, c_int, c_void_p, c_void_p, c_long,

@@ -7,6 +7,7 @@
 #include "kernels.cuh"
 #include "workspace.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <new>
@@ -57,11 +58,7 @@ int munk_workspace_create(int device, munk_workspace_t** out) {
 int munk_workspace_destroy(munk_workspace_t* ws) {
   if (!ws) return MUNK_OK;
   cudaSetDevice(ws->device);
-  if (ws->splitk) cudaFree(ws->splitk);
-  if (ws->linv) cudaFree(ws->linv);
-  if (ws->tmp) cudaFree(ws->tmp);
-  if (ws->info) cudaFree(ws->info);
-  if (ws->info_host) cudaFreeHost(ws->info_host);
+  ws->release();
   delete ws;
   return MUNK_OK;
 }
@@ -83,8 +80,8 @@ int munk_assemble_reglap(munk_workspace_t* ws, int n, int nnz, const int* u, con
   if (nnz < 0) return -3;
   if (ld < n) return -8;
   // degree scratch: reuse the split-K buffer (never live at the same time on one stream)
-  MUNK_TRY(ws->ensure(&ws->splitk, &ws->splitk_bytes, (size_t)(n + 2) * sizeof(int)));
-  MUNK_TRY(assemble_reglap(n, nnz, u, v, lam, A, ld, (int*)ws->splitk, S(stream)));
+  MUNK_TRY(ws->ensure_splitk(0, std::max(SPLITK_RESERVE, (size_t)(n + 2) * sizeof(int))));
+  MUNK_TRY(assemble_reglap(n, nnz, u, v, lam, A, ld, (int*)ws->splitk[0], S(stream)));
   ws->launches += (nnz > 0) ? 3 : 1;
   return MUNK_OK;
 }
@@ -112,6 +109,21 @@ int munk_trtri(munk_workspace_t* ws, int n, double* L, long ld, double* linv, vo
   if (ld < n || (ld & 1)) return -4;
   if (!L || !linv) return -3;
   return trtri_lower(ws, n, L, ld, linv, S(stream));
+}
+
+int munk_trsm_left(munk_workspace_t* ws, int n, const double* L, long ld, const double* linv,
+                   int transposed, int nrhs, double* B, long ldb, void* stream) {
+  if (!ws) return -1;
+  if (n < 0) return -2;
+  if (ld < n || (ld & 1)) return -4;
+  if (nrhs < 0) return -7;
+  if (ldb < nrhs || (ldb & 1)) return -9;
+  return trsm_left(ws, n, L, ld, linv, transposed, nrhs, B, ldb, S(stream));
+}
+
+int munk_transpose(int rows, int cols, const double* in, long ldi, double* out, long ldo,
+                   void* stream) {
+  return transpose_general(rows, cols, in, ldi, out, ldo, S(stream));
 }
 
 int munk_gram_lower(munk_workspace_t* ws, int n, const double* W, long ldw, double* D, long ldd,

@@ -84,6 +84,22 @@ __global__ void transpose_lower_kernel(int n, const double* __restrict__ in, lon
   }
 }
 
+// out[c][r] = in[r][c]
+__global__ void transpose_kernel(int rows, int cols, const double* __restrict__ in, long ldi,
+                                 double* __restrict__ out, long ldo) {
+  __shared__ double tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+    const int r = r0 + ty, c = c0 + threadIdx.x;
+    tile[ty][threadIdx.x] = (r < rows && c < cols) ? in[(long)r * ldi + c] : 0.0;
+  }
+  __syncthreads();
+  for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+    const int c = c0 + ty, r = r0 + threadIdx.x;     // out row = c, out col = r
+    if (c < cols && r < rows) out[(long)c * ldo + r] = tile[threadIdx.x][ty];
+  }
+}
+
 __global__ void copy_lower_kernel(int n, const double* __restrict__ in, long ldi,
                                   double* __restrict__ out, long ldo) {
   const int r = blockIdx.x;
@@ -150,6 +166,15 @@ int transpose_lower(int n, const double* in, long ldi, double* out, long ldo, cu
   if (n <= 0) return MUNK_OK;
   dim3 grid((n + 31) / 32, (n + 31) / 32);
   transpose_lower_kernel<<<grid, dim3(32, 8), 0, stream>>>(n, in, ldi, out, ldo);
+  MUNK_CUDA_TRY(cudaGetLastError());
+  return MUNK_OK;
+}
+
+int transpose_general(int rows, int cols, const double* in, long ldi, double* out, long ldo,
+                      cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return MUNK_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(rows, cols, in, ldi, out, ldo);
   MUNK_CUDA_TRY(cudaGetLastError());
   return MUNK_OK;
 }

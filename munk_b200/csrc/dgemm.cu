@@ -43,6 +43,7 @@ struct KernelArgs {
   double* ws;       // split-K partials, slice z at ws + z * ws_slice, row stride ws_ld
   long ws_slice;
   long ws_ld;
+  int mt, nt, gn;   // tile grid and rasterisation strip width (in tiles)
 };
 
 // k index (0..15 inside a stage) read by lane-quad position j = lane & 3 at sub-step s:
@@ -76,8 +77,21 @@ template <bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                       const __grid_constant__ CUtensorMap tmB, const KernelArgs g) {
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
+  // Tile rasterisation: strips of `gn` tile columns, tile rows fastest inside a strip, so a wave
+  // of 148 CTAs covers about 12 x 12 tiles and shares 12 + 12 operand panels through L2 instead
+  // of 148 + 1 (the m-fastest order re-streamed all of A once per tile column: 210 GB of DRAM
+  // reads for the C3 score product, profiles/r01_ncu_summary.md).
+  int tile_m, tile_n;
+  {
+    const int per = g.gn * g.mt;
+    const int strip = (int)blockIdx.x / per;
+    const int rem = (int)blockIdx.x - strip * per;
+    const int width = min(g.gn, g.nt - strip * g.gn);
+    tile_m = rem / width;
+    tile_n = strip * g.gn + (rem - tile_m * width);
+  }
+  const int m0 = tile_m * BM;
+  const int n0 = tile_n * BN;
   if ((g.flags & GF_TILE_LOWER) && n0 >= m0 + BM) return;
 
   // k-range of this tile, in 16-deep iterations.
@@ -347,7 +361,7 @@ double gemm_flops(const GemmDesc& g) {
   return f;
 }
 
-int gemm_launch(Workspace* ws, const GemmDesc& g, cudaStream_t stream) {
+int gemm_launch(Workspace* ws, const GemmDesc& g, cudaStream_t stream, int scratch) {
   if (g.M <= 0 || g.N <= 0) return MUNK_OK;
   if (((uintptr_t)g.C & 15) || (g.ldc & 1)) {
     set_last_error("GEMM output must be 16-byte aligned with an even leading dimension");
@@ -381,21 +395,25 @@ int gemm_launch(Workspace* ws, const GemmDesc& g, cudaStream_t stream) {
   ka.flags = g.flags;
   ka.nsplit = 1; ka.ws = nullptr; ka.ws_slice = 0; ka.ws_ld = 0;
 
-  // Split-K when the tile grid cannot fill 148 SMs and the contraction is long.
+  // Split-K whenever the tile grid cannot fill the 148 SMs: one 128x128 tile advances only 16 of
+  // k every ~2 us (DMMA rate of one SM), so the small and mid-size products on the critical path
+  // of the recursive factorisations are latency-bound unless their k-range is spread out.
+  // Each split keeps at least 2 k-iterations; partials are reduced in a fixed order.
   int nsplit = 1;
-  if (ws && active > 0 && active <= 74 && max_it >= 64 && !(g.flags & GF_SYM_MIRROR)) {
-    nsplit = (int)std::min<long>(148 / active, max_it / 32);
-    nsplit = std::max(1, std::min(nsplit, 64));
+  if (ws && active > 0 && active <= 111 && max_it >= 4 && !(g.flags & GF_SYM_MIRROR)) {
+    nsplit = (int)std::min<long>((148 + active - 1) / active, max_it / 2);
+    nsplit = std::max(1, std::min(nsplit, 74));
   }
   if (nsplit > 1) {
     ka.nsplit = nsplit;
     ka.ws_ld = round_up(g.N, 2);
     ka.ws_slice = (long)g.M * ka.ws_ld;
-    MUNK_TRY(ws->ensure(&ws->splitk, &ws->splitk_bytes, (size_t)nsplit * ka.ws_slice * 8));
-    ka.ws = ws->splitk;
+    MUNK_TRY(ws->ensure_splitk(scratch, std::max(SPLITK_RESERVE, (size_t)nsplit * ka.ws_slice * 8)));
+    ka.ws = ws->splitk[scratch];
   }
 
-  dim3 grid(mt, nt, nsplit);
+  ka.mt = mt; ka.nt = nt; ka.gn = std::min(nt, 12);
+  dim3 grid((unsigned)(mt * nt), 1, nsplit);
   int st;
   if (g.a_layout == OP_KC && g.b_layout == OP_KC) st = launch_variant<true, true>(ta, tb, ka, grid, stream);
   else if (g.a_layout == OP_KC) st = launch_variant<true, false>(ta, tb, ka, grid, stream);

@@ -31,7 +31,9 @@ struct Workspace;  // api.cu
 
 // C = alpha * A(M x K) * B(N x K)^T + beta * C on `stream`.  All pointers device, 16-byte
 // aligned, lda/ldb/ldc even.  Returns a MUNK_* status.
-int gemm_launch(Workspace* ws, const GemmDesc& g, cudaStream_t stream);
+// `scratch` selects the split-K buffer: 0 for the caller's stream, 1 for the workspace's
+// look-ahead stream (two launches that may run concurrently must not share one).
+int gemm_launch(Workspace* ws, const GemmDesc& g, cudaStream_t stream, int scratch = 0);
 
 // Flops actually executed as useful work by gemm_launch for this descriptor (tile-granular).
 double gemm_flops(const GemmDesc& g);

@@ -1,19 +1,24 @@
-// Recursive blocked Cholesky / triangular inverse on one GPU.
+// Blocked Cholesky / triangular inverse on one GPU.
 //
 // Replaces the LAPACK calls behind munk/munk/munk.py:83 (np.linalg.inv of I + lam*L) and
 // munk/munk/munk.py:87-88 (scipy.linalg.eigh + diag GEMM): A = L L^T is SPD (eigenvalues >= 1),
 // so D = A^-1 = W^T W with W = L^-1, and C = W^T is an RKHS factor (C C^T = D) without an
 // eigensolver.
 //
-// Right-looking recursion, all matrices row-major, lower triangle, in place:
-//   potrf(A):  potrf(A11);  A21 <- A21 L11^-T (trsm);  A22 <- A22 - A21 A21^T (DMMA syrk);
-//              potrf(A22)
-//   trsm(B,L): B1 <- trsm(B1,L11);  B2 <- B2 - B1 L21^T (DMMA gemm);  B2 <- trsm(B2,L22)
-//   trtri(L):  W11 = trtri(L11); W22 = trtri(L22); W21 = -W22 (L21 W11)   (two DMMA trmm)
-// Every split is a multiple of 128, so the recursion bottoms out on aligned 128x128 diagonal
-// blocks.  One CTA factors such a block in shared memory and also inverts it; the inverse is
-// kept (Workspace::linv) and turns the leaf trsm into a DMMA product and the leaf trtri
-// into a copy.
+// All matrices row-major, lower triangle, in place.  Building blocks (recursive, every split a
+// multiple of 128, so they bottom out on aligned 128x128 diagonal blocks):
+//   potrf_rec(A):  potrf(A11);  A21 <- A21 L11^-T (trsm);  A22 <- A22 - A21 A21^T (DMMA syrk);
+//                  potrf(A22)
+//   trsm_rec(B,L): B1 <- trsm(B1,L11);  B2 <- B2 - B1 L21^T (DMMA gemm);  B2 <- trsm(B2,L22)
+//   trtri_rec(L):  W11 = trtri(L11); W22 = trtri(L22); W21 = -W22 (L21 W11)   (two DMMA trmm)
+// One CTA factors a 128x128 diagonal block and also inverts it (leaf.cu); the inverse is kept
+// (`linv`) and turns the leaf trsm into a DMMA product and the leaf trtri into a copy.
+//
+// Large matrices use the right-looking blocked driver potrf_lookahead(): panels of 512 columns,
+// the panel work (look-ahead update of the next block column, its recursive factorisation and
+// panel solve: many small, latency-bound launches) runs on a high-priority side stream while the
+// caller's stream applies the previous panel to the rest of the trailing matrix (one big DMMA
+// syrk per panel), so the latency-bound part is hidden behind tensor-core work.
 #include "dgemm.cuh"
 #include "factor.cuh"
 #include "leaf.cuh"
@@ -26,6 +31,7 @@ namespace munk {
 namespace {
 
 constexpr int LEAF = MUNK_LEAF;
+constexpr int PANEL = 512;          // block-column width of the look-ahead driver
 
 // dst (nb x nb block inside a row-major matrix) <- src (128-ld leaf inverse)
 __global__ void copy_leaf_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ src,
@@ -47,6 +53,7 @@ struct Rec {
   Workspace* ws;
   cudaStream_t stream;
   double* linv;      // leaf inverses of this matrix, block g at linv + g*128*128
+  int scratch;       // split-K buffer of `stream` (0 caller's stream, 1 side stream)
 };
 
 int leaf_potrf(Rec& r, double* A, long ld, int nb, int gidx) {
@@ -67,7 +74,7 @@ int trsm_rec(Rec& r, double* B, long ldb, int m, const double* L, long ldl, int 
     g.B = r.linv + (long)(gidx / LEAF) * LEAF * LEAF; g.ldb = LEAF; g.b_layout = OP_KC;
     g.C = B; g.ldc = ldb;     // in place: N <= 128, so each CTA owns its rows completely
     g.alpha = 1.0; g.beta = 0.0; g.flags = GF_KHI_N;
-    return gemm_launch(r.ws, g, r.stream);
+    return gemm_launch(r.ws, g, r.stream, r.scratch);
   }
   const int s1 = split_point(s), s2 = s - s1;
   MUNK_TRY(trsm_rec(r, B, ldb, m, L, ldl, s1, gidx));
@@ -77,8 +84,20 @@ int trsm_rec(Rec& r, double* B, long ldb, int m, const double* L, long ldl, int 
   g.B = L + (long)s1 * ldl; g.ldb = ldl; g.b_layout = OP_KC;     // L21
   g.C = B + s1; g.ldc = ldb;
   g.alpha = -1.0; g.beta = 1.0; g.flags = 0;
-  MUNK_TRY(gemm_launch(r.ws, g, r.stream));
+  MUNK_TRY(gemm_launch(r.ws, g, r.stream, r.scratch));
   return trsm_rec(r, B + s1, ldb, m, L + (long)s1 * ldl + s1, ldl, s2, gidx + s1);
+}
+
+// C (lower tiles of an m x nc block whose top nc x nc part is diagonal) -= X Y^T, K = k
+int syrk_update(Rec& r, double* C, long ldc, int m, int nc, const double* X, const double* Y, long ldx,
+                int k) {
+  GemmDesc g{};
+  g.M = m; g.N = nc; g.K = k;
+  g.A = X; g.lda = ldx; g.a_layout = OP_KC;
+  g.B = Y; g.ldb = ldx; g.b_layout = OP_KC;
+  g.C = C; g.ldc = ldc;
+  g.alpha = -1.0; g.beta = 1.0; g.flags = GF_TILE_LOWER;
+  return gemm_launch(r.ws, g, r.stream, r.scratch);
 }
 
 int potrf_rec(Rec& r, double* A, long ld, int n, int gidx) {
@@ -88,14 +107,64 @@ int potrf_rec(Rec& r, double* A, long ld, int n, int gidx) {
   double* A21 = A + (long)n1 * ld;
   double* A22 = A21 + n1;
   MUNK_TRY(trsm_rec(r, A21, ld, n2, A, ld, n1, gidx));
-  GemmDesc g{};
-  g.M = n2; g.N = n2; g.K = n1;
-  g.A = A21; g.lda = ld; g.a_layout = OP_KC;
-  g.B = A21; g.ldb = ld; g.b_layout = OP_KC;
-  g.C = A22; g.ldc = ld;
-  g.alpha = -1.0; g.beta = 1.0; g.flags = GF_TILE_LOWER;
-  MUNK_TRY(gemm_launch(r.ws, g, r.stream));
+  MUNK_TRY(syrk_update(r, A22, ld, n2, n2, A21, A21, ld, n1));
   return potrf_rec(r, A22, ld, n2, gidx + n1);
+}
+
+// Right-looking blocked Cholesky with one panel of look-ahead on the side stream.
+//   step j (panel j = columns [c0, c0+w) already factored, event panel[j]):
+//     side stream : wait upd[j-1];  block column j+1 -= panel j contributions (look-ahead);
+//                   factor panel j+1 (potrf_rec of its diagonal block + trsm_rec below);
+//                   record panel[j+1]
+//     main stream : wait panel[j];  columns beyond block column j+1 -= panel j contributions
+//                   (one lower-tile DMMA syrk, K = w);  record upd[j]
+int potrf_lookahead(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t main) {
+  const int nblk = (n + PANEL - 1) / PANEL;
+  MUNK_TRY(ws->ensure_side(2 * (size_t)nblk + 2));
+  MUNK_TRY(ws->ensure_splitk(0, SPLITK_RESERVE));
+  MUNK_TRY(ws->ensure_splitk(1, SPLITK_RESERVE));
+  cudaStream_t side = ws->side;
+  cudaEvent_t* panel_ev = ws->events.data();          // [nblk]
+  cudaEvent_t* upd_ev = ws->events.data() + nblk;     // [nblk]
+  cudaEvent_t fork_ev = ws->events[2 * nblk];
+  Rec rs{ws, side, linv, 1}, rm{ws, main, linv, 0};
+
+  auto factor_panel = [&](int c0, int w) -> int {
+    double* diag = A + (long)c0 * ld + c0;
+    MUNK_TRY(potrf_rec(rs, diag, ld, w, c0));
+    const int below = n - (c0 + w);
+    if (below > 0) MUNK_TRY(trsm_rec(rs, diag + (long)w * ld, ld, below, diag, ld, w, c0));
+    return MUNK_OK;
+  };
+
+  MUNK_CUDA_TRY(cudaEventRecord(fork_ev, main));
+  MUNK_CUDA_TRY(cudaStreamWaitEvent(side, fork_ev, 0));
+  MUNK_TRY(factor_panel(0, std::min(PANEL, n)));
+  MUNK_CUDA_TRY(cudaEventRecord(panel_ev[0], side));
+
+  int last_panel = 0;
+  for (int j = 0; j + 1 < nblk; ++j) {
+    const int c0 = j * PANEL, w = PANEL;              // every panel but the last is full width
+    const int r1 = c0 + w;                            // first row/column of block column j+1
+    const int w1 = std::min(PANEL, n - r1);
+    const int r2 = r1 + w1;                           // first column the main stream updates
+    const double* pan = A + (long)r1 * ld + c0;       // panel j rows >= r1
+    // side: look-ahead update of block column j+1, then its factorisation
+    if (j > 0) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, upd_ev[j - 1], 0));
+    MUNK_TRY(syrk_update(rs, A + (long)r1 * ld + r1, ld, n - r1, w1, pan, pan, ld, w));
+    MUNK_TRY(factor_panel(r1, w1));
+    MUNK_CUDA_TRY(cudaEventRecord(panel_ev[j + 1], side));
+    last_panel = j + 1;
+    // main: the rest of the trailing matrix
+    MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[j], 0));
+    if (r2 < n) {
+      const double* pan2 = A + (long)r2 * ld + c0;    // panel j rows >= r2
+      MUNK_TRY(syrk_update(rm, A + (long)r2 * ld + r2, ld, n - r2, n - r2, pan2, pan2, ld, w));
+    }
+    MUNK_CUDA_TRY(cudaEventRecord(upd_ev[j], main));
+  }
+  MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[last_panel], 0));   // join
+  return MUNK_OK;
 }
 
 int trtri_rec(Rec& r, double* L, long ld, int n, int gidx) {
@@ -117,7 +186,7 @@ int trtri_rec(Rec& r, double* L, long ld, int n, int gidx) {
   g.B = L; g.ldb = ld; g.b_layout = OP_MC;
   g.C = r.ws->tmp; g.ldc = ldt;
   g.alpha = 1.0; g.beta = 0.0; g.flags = GF_KLO_N;
-  MUNK_TRY(gemm_launch(r.ws, g, r.stream));
+  MUNK_TRY(gemm_launch(r.ws, g, r.stream, r.scratch));
   // W21 = -W22 * T  (W22 lower: k <= row)
   GemmDesc h{};
   h.M = n2; h.N = n1; h.K = n2;
@@ -125,16 +194,61 @@ int trtri_rec(Rec& r, double* L, long ld, int n, int gidx) {
   h.B = r.ws->tmp; h.ldb = ldt; h.b_layout = OP_MC;
   h.C = L21; h.ldc = ld;
   h.alpha = -1.0; h.beta = 0.0; h.flags = GF_KHI_M;
-  return gemm_launch(r.ws, h, r.stream);
+  return gemm_launch(r.ws, h, r.stream, r.scratch);
+}
+
+// Left solves with the Cholesky factor, in place on the row-major n x r block B:
+//   forward : L X = B        X1 = fwd(L11,B1); B2 -= L21 X1;   X2 = fwd(L22,B2)
+//   backward: L^T X = B      X2 = bwd(L22,B2); B1 -= L21^T X2; X1 = bwd(L11,B1)
+// Leaves multiply by the stored inverse of the 128x128 diagonal block (M <= 128, so a CTA reads
+// and writes only its own column strip of B: safe in place).
+int trsm_left_rec(Rec& r, const double* L, long ldl, int n, double* B, long ldb, int nrhs, int gidx,
+                  bool transposed) {
+  if (n <= LEAF) {
+    GemmDesc g{};
+    g.M = n; g.N = nrhs; g.K = n;
+    g.A = r.linv + (long)(gidx / LEAF) * LEAF * LEAF; g.lda = LEAF;
+    g.a_layout = transposed ? OP_MC : OP_KC;
+    g.B = B; g.ldb = ldb; g.b_layout = OP_MC;
+    g.C = B; g.ldc = ldb;
+    g.alpha = 1.0; g.beta = 0.0; g.flags = transposed ? GF_KLO_M : GF_KHI_M;
+    return gemm_launch(r.ws, g, r.stream, r.scratch);
+  }
+  const int n1 = split_point(n), n2 = n - n1;
+  const double* L21 = L + (long)n1 * ldl;
+  const double* L22 = L21 + n1;
+  double* B2 = B + (long)n1 * ldb;
+  GemmDesc g{};
+  g.alpha = -1.0; g.beta = 1.0; g.flags = 0;
+  g.A = L21; g.lda = ldl;
+  g.ldb = ldb; g.b_layout = OP_MC; g.ldc = ldb; g.N = nrhs;
+  if (!transposed) {
+    MUNK_TRY(trsm_left_rec(r, L, ldl, n1, B, ldb, nrhs, gidx, false));
+    g.M = n2; g.K = n1; g.a_layout = OP_KC; g.B = B; g.C = B2;          // B2 -= L21 X1
+    MUNK_TRY(gemm_launch(r.ws, g, r.stream, r.scratch));
+    return trsm_left_rec(r, L22, ldl, n2, B2, ldb, nrhs, gidx + n1, false);
+  }
+  MUNK_TRY(trsm_left_rec(r, L22, ldl, n2, B2, ldb, nrhs, gidx + n1, true));
+  g.M = n1; g.K = n2; g.a_layout = OP_MC; g.B = B2; g.C = B;            // B1 -= L21^T X2
+  MUNK_TRY(gemm_launch(r.ws, g, r.stream, r.scratch));
+  return trsm_left_rec(r, L, ldl, n1, B, ldb, nrhs, gidx, true);
 }
 
 }  // namespace
+
+int trsm_left(Workspace* ws, int n, const double* L, long ld, const double* linv, int transposed,
+              int nrhs, double* B, long ldb, cudaStream_t stream) {
+  if (n <= 0 || nrhs <= 0) return MUNK_OK;
+  Rec r{ws, stream, const_cast<double*>(linv), 0};
+  return trsm_left_rec(r, L, ld, n, B, ldb, nrhs, 0, transposed != 0);
+}
 
 size_t linv_bytes_for(int n) { return (size_t)((n + LEAF - 1) / LEAF) * LEAF * LEAF * 8; }
 
 int potrf_lower(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t stream) {
   if (n <= 0) return MUNK_OK;
-  Rec r{ws, stream, linv};
+  if (n > 2 * PANEL) return potrf_lookahead(ws, n, A, ld, linv, stream);
+  Rec r{ws, stream, linv, 0};
   return potrf_rec(r, A, ld, n, 0);
 }
 
@@ -146,7 +260,7 @@ int trtri_lower(Workspace* ws, int n, double* L, long ld, double* linv, cudaStre
     // the top-level temporary is the largest one of the recursion (n2 <= n1 at every level)
     MUNK_TRY(ws->ensure(&ws->tmp, &ws->tmp_bytes, std::max(need, (size_t)n1 * round_up(n1, 16) * 8)));
   }
-  Rec r{ws, stream, linv};
+  Rec r{ws, stream, linv, 0};
   return trtri_rec(r, L, ld, n, 0);
 }
 

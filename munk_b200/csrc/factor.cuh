@@ -18,4 +18,9 @@ int potrf_lower(Workspace* ws, int n, double* A, long ld, double* linv, cudaStre
 // In-place inverse of the lower-triangular factor produced by potrf_lower (same linv).
 int trtri_lower(Workspace* ws, int n, double* L, long ld, double* linv, cudaStream_t stream);
 
+// B (n x nrhs, row-major, in place) <- L^-1 B (transposed = 0) or L^-T B (transposed = 1), with
+// the factor and leaf inverses left by potrf_lower.
+int trsm_left(Workspace* ws, int n, const double* L, long ld, const double* linv, int transposed,
+              int nrhs, double* B, long ldb, cudaStream_t stream);
+
 }  // namespace munk

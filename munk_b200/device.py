@@ -215,6 +215,33 @@ class Device:
         self.gemm(KC, MC, n1, n2, kq, 1.0, Q1, Z, 0.0, P, 0)           # P = M^T Z
         return P
 
+    def trsm_left(self, L, n, linv, B, nrhs, transposed):
+        """B[:n, :nrhs] <- L^-1 B or L^-T B in place (factor + leaf inverses from potrf)."""
+        check(lib.munk_trsm_left(self._ws, n, _ptr(L), L.stride(0), _ptr(linv), 1 if transposed else 0,
+                                 nrhs, _ptr(B), B.stride(0), self.stream()), "munk_trsm_left")
+        return B
+
+    def transpose(self, X, rows, cols):
+        out = self.empty(cols, rows)
+        check(lib.munk_transpose(rows, cols, _ptr(X), X.stride(0), _ptr(out), out.stride(0),
+                                 self.stream()), "munk_transpose")
+        return out
+
+    def target_landmark_rows_from_factor(self, L2, linv2, n2, target_idx):
+        """B = D2[Lt, :] = (A2^-1 E_Lt)^T from the Cholesky factor alone: two triangular solves
+        with k right-hand sides (2 n2^2 k flops) instead of the full inverse (2 n2^3 / 3)."""
+        if torch.is_tensor(target_idx):
+            k, rows = int(target_idx.numel()), target_idx.to(self.torch_device).long()
+        else:
+            k = len(target_idx)
+            rows = torch.as_tensor(np.asarray(target_idx, dtype=np.int64), device=self.torch_device)
+        X = torch.zeros((n2, pad16(k)), dtype=torch.float64, device=self.torch_device)
+        cols = torch.arange(k, device=self.torch_device)
+        X[rows, cols] = 1.0
+        self.trsm_left(L2, n2, linv2, X, k, transposed=False)
+        self.trsm_left(L2, n2, linv2, X, k, transposed=True)
+        return self.transpose(X, n2, k)
+
     def target_landmark_rows(self, W2, n2, target_idx):
         """B = D2[Lt, :] = (W2[:, Lt])^T W2 without forming D2 (k x n2)."""
         Q2 = self.gather_cols_lower(W2, n2, target_idx)

@@ -4,8 +4,8 @@ This is what `embed_networks` (munk/munk/munk.py:114-176) followed by the score 
 (scripts/compute_embeddings.py:81) computes, restructured so that nothing round-trips through
 the host between the stages:
 
-    W1 = chol(I + lam L1)^-1, W2 = chol(I + lam L2)^-1          (C1 = W1^T, D2 = W2^T W2)
-    Q1 = W1[:, Ls']  (= C1[Ls',:]^T, duplicates of Ls folded)    B = D2[Lt,:] = W2[:,Lt]^T W2
+    W1 = chol(I + lam L1)^-1 (C1 = W1^T),  L2 = chol(I + lam L2)
+    Q1 = W1[:, Ls']  (= C1[Ls',:]^T, duplicates of Ls folded)    B = D2[Lt,:] = (L2^-T L2^-1 E_Lt)^T
     P  = C2hat^T = Q1 (Q1^T Q1)^-1 mean_groups(B)               S = W1^T P
 """
 import time
@@ -46,9 +46,9 @@ class _Phase:
 class DeviceEmbedding:
     """Result of embed_device(): everything still on the GPU."""
 
-    def __init__(self, dev, n1, n2, W1, W2, P, runtimes):
+    def __init__(self, dev, n1, n2, W1, L2, P, runtimes):
         self.dev, self.n1, self.n2 = dev, n1, n2
-        self.W1, self.W2, self.P = W1, W2, P
+        self.W1, self.L2, self.P = W1, L2, P          # L2: Cholesky factor of the target (or None)
         self.runtimes = runtimes
         self._S = None
 
@@ -88,13 +88,13 @@ def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.
         del linv1
     with timer("target_regularized_laplacian_runtime"):
         A2 = dev.assemble(n2, edges2[0], edges2[1], tgt_lam)
-        W2 = dev.inverse_factor(A2, n2)
+        linv2 = dev.potrf(A2, n2)
     with timer("embed_runtime"):
         Q1 = dev.gather_cols_lower(W1, n1, uniq)
-        B = dev.target_landmark_rows(W2, n2, t_idx)
+        B = dev.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
         P = dev.project(Q1, n1, B, n2, (gptr, members))
         dev.raise_if_not_spd()
-    return DeviceEmbedding(dev, n1, n2, W1, W2 if keep_target_factor else None, P, timer.times)
+    return DeviceEmbedding(dev, n1, n2, W1, A2 if keep_target_factor else None, P, timer.times)
 
 
 def graph_inputs(source_G, target_G, homologs, n_landmarks):

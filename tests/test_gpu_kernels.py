@@ -1,0 +1,181 @@
+"""Kernel-level GPU tests through the C ABI: GEMM layouts and structure flags, factorisations,
+triangular solves, permutation-test unit.  torch float64 on the same device is the checker for
+the linear algebra; the oracle is the checker for the permutation statistic."""
+import numpy as np
+import pytest
+
+from oracle import munk_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from munk_b200.device import default_device
+    return default_device()
+
+
+def relerr(x, y):
+    return float((x - y).abs().max() / y.abs().max())
+
+
+def spd(n, seed):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    X = torch.randn(n, n, dtype=torch.float64, generator=g).cuda()
+    return X @ X.t() / n + 2.0 * torch.eye(n, dtype=torch.float64, device="cuda")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (200, 150, 100), (130, 70, 33), (1000, 900, 1100),
+                                   (64, 64, 2000), (400, 400, 5000), (17, 1, 5), (2000, 300, 640)])
+def test_gemm_all_layouts(dev, M, N, K):
+    """C = alpha A B^T + beta C for both storages of either operand, ragged sizes, padded ld,
+    including shapes that take the split-K path."""
+    import torch
+    from munk_b200.device import KC, MC
+    torch.manual_seed(M + N + K)
+    for al in (KC, MC):
+        for bl in (KC, MC):
+            A = torch.randn(M, K, dtype=torch.float64, device="cuda")
+            B = torch.randn(N, K, dtype=torch.float64, device="cuda")
+            Ab = dev.empty(M, K) if al == KC else dev.empty(K, M)
+            Bb = dev.empty(N, K) if bl == KC else dev.empty(K, N)
+            Ab.zero_(); Bb.zero_()
+            (Ab[:, :K] if al == KC else Ab[:, :M]).copy_(A if al == KC else A.t())
+            (Bb[:, :K] if bl == KC else Bb[:, :N]).copy_(B if bl == KC else B.t())
+            C0 = torch.randn(M, N + (N & 1) + 2, dtype=torch.float64, device="cuda")
+            for alpha, beta in ((1.0, 0.0), (-1.0, 1.0), (0.5, 2.0)):
+                C = C0.clone()
+                dev.gemm(al, bl, M, N, K, alpha, Ab, Bb, beta, C)
+                ref = alpha * (A @ B.t()) + beta * C0[:, :N]
+                assert relerr(C[:, :N], ref) < 1e-12
+                assert torch.equal(C[:, N:], C0[:, N:])          # padding untouched
+
+
+def test_gemm_structure_flags_never_read_stale_blocks(dev):
+    """Triangular k-ranges are clipped per 128-tile: NaNs planted in the blocks above the diagonal
+    must never reach a result."""
+    import torch
+    from munk_b200.device import KC, MC, KLO_M, KLO_N, KHI_M, KHI_N
+    n = 700
+    torch.manual_seed(1)
+    W = torch.tril(torch.randn(n, n, dtype=torch.float64, device="cuda"))
+    blk = torch.arange(n, device="cuda") // 128
+    Wg = W.clone()
+    Wg[blk[:, None] < blk[None, :]] = float("nan")
+    D = dev.gram_lower(Wg, n, ld=n)
+    assert relerr(D, W.t() @ W) < 1e-13 and torch.equal(D, D.t())
+    P = torch.randn(n, 500, dtype=torch.float64, device="cuda")
+    X = torch.randn(300, n, dtype=torch.float64, device="cuda")
+    out = dev.empty(n, 500, ld=500)
+    dev.gemm(MC, MC, n, 500, n, 1.0, Wg, P, 0.0, out, KLO_M)
+    assert relerr(out, W.t() @ P) < 1e-13
+    dev.gemm(KC, MC, n, 500, n, 1.0, Wg, P, 0.0, out, KHI_M)
+    assert relerr(out, W @ P) < 1e-13
+    out2 = dev.empty(300, n, ld=n)
+    dev.gemm(KC, MC, 300, n, n, 1.0, X, Wg, 0.0, out2, KLO_N)
+    assert relerr(out2, X @ W) < 1e-13
+    dev.gemm(KC, KC, 300, n, n, 1.0, X, Wg, 0.0, out2, KHI_N)
+    assert relerr(out2, X @ W.t()) < 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 64, 128, 129, 300, 1000, 1300, 2500, 4000])
+def test_potrf_trtri_trsm(dev, n):
+    """Cholesky (recursive below 1024, look-ahead driver above), triangular inverse, W^T W and the
+    left solves against torch on the same matrix."""
+    import torch
+    A0 = spd(n, n)
+    A = dev.empty(n, n)
+    A[:, :n] = A0
+    linv = dev.potrf(A, n)
+    L = torch.tril(A[:, :n])
+    Lref = torch.linalg.cholesky(A0)
+    assert relerr(L, Lref) < 1e-12
+    rhs = torch.randn(n, 37, dtype=torch.float64, device="cuda")
+    B = dev.empty(n, 37)
+    B[:, :37] = rhs
+    dev.trsm_left(A, n, linv, B, 37, transposed=False)
+    assert relerr(Lref @ B[:, :37], rhs) < 1e-11
+    B[:, :37] = rhs
+    dev.trsm_left(A, n, linv, B, 37, transposed=True)
+    assert relerr(Lref.t() @ B[:, :37], rhs) < 1e-11
+    dev.trtri(A, n, linv)
+    W = torch.tril(A[:, :n])
+    eye = torch.eye(n, dtype=torch.float64, device="cuda")
+    assert relerr(W @ Lref, eye) < 1e-11
+    D = dev.gram_lower(A, n)
+    assert relerr(D[:, :n] @ A0, eye) < 1e-11
+
+
+def test_potrf_reports_first_bad_pivot(dev):
+    import torch
+    from munk_b200.device import NotPositiveDefinite
+    A = dev.empty(300, 300)
+    A.zero_()
+    A[:, :300] = torch.eye(300, dtype=torch.float64, device="cuda")
+    A[200, 200] = -1.0
+    with pytest.raises(NotPositiveDefinite) as err:
+        dev.potrf(A, 300)
+    assert "pivot 200" in str(err.value)
+    assert dev.potrf_info() == 0                                   # flag is cleared once read
+
+
+def test_target_rows_from_factor_equals_inverse_rows(dev):
+    import networkx as nx
+    import torch
+    from munk_b200 import util
+    n = 900
+    G = nx.barabasi_albert_graph(n, 6, seed=9)
+    u, v = util.edge_index_arrays(G, list(range(n)))
+    idx = [5, 880, 0, 5, 431]
+    A = dev.assemble(n, u, v, 0.05)
+    linv = dev.potrf(A, n)
+    B = dev.target_landmark_rows_from_factor(A, linv, n, idx)
+    D = np.linalg.inv(oracle.reglap_matrix(n, oracle.edge_index_arrays(G, list(range(n))), 0.05))
+    assert oracle.rel_max_err(B[:len(idx), :n].cpu().numpy(), D[idx, :]) < 1e-12
+    W = dev.trtri(A, n, linv)
+    B2 = dev.target_landmark_rows(W, n, idx)
+    assert oracle.rel_max_err(B2[:len(idx), :n].cpu().numpy(), D[idx, :]) < 1e-12
+
+
+def test_permutation_unit_and_experiment(dev):
+    """difference_in_means (permtest.py:68-80) on host arrays vs the oracle, and the sharded
+    experiment in 'indices' mode vs the oracle run permutation by permutation."""
+    from munk_b200 import permtest, synthetic
+    G1, G2, homs = synthetic.make_case(260, 220, 4, 60, seeds=(31, 32))
+    k = 15
+    ref = oracle.embed_networks(G1, G2, homs, k)
+    src = dict(C=ref["C1"], nodes=ref["source_nodes"])
+    tgt = dict(D=ref["D2"], nodes=ref["target_nodes"])
+    got = permtest.difference_in_means(src, tgt, homs, k, ref["source_nodes"], ref["target_nodes"])
+    want = oracle.difference_in_means(ref["C1"], ref["D2"], ref["homolog_idxs"], k)
+    assert np.allclose(got, want, rtol=1e-10, atol=0)
+    res = permtest.run_permutation_test(G1, G2, homs, k, n_permutations=6, mode="indices")
+    assert res["errs"] == 0 and res["n_permutations"] == 6.0
+    assert abs(res["real"]["mean_diff"] - want[0]) <= 1e-10 * abs(want[0])
+    diffs = []
+    for p in range(6):
+        perm = permtest.permuted_homolog_idxs(ref["homolog_idxs"], p)
+        diffs.append(oracle.difference_in_means(ref["C1"], ref["D2"], perm, k)[0])
+    assert np.allclose(res["random"]["mean_diffs"], diffs, rtol=1e-9, atol=0)
+    pval, n_less, n_obs = oracle.one_tail_pval(want[0], np.array(diffs))
+    assert (res["pval"], res["n_less_than"]) == (pval, n_less)
+    assert abs(res["effect_size"] - oracle.effect_size(want[0], np.array(diffs))) < 1e-6 * abs(res["effect_size"])
+
+
+def test_random_network_generator(dev):
+    """gen_random_network_data (gen_random_network.py:78-84): same nodes and degrees as the seed
+    graph, D and C consistent with the oracle on the generated graph."""
+    import networkx as nx
+    from munk_b200 import permtest, synthetic
+    seed_G = oracle.simple_two_core(synthetic.ba_graph(150, 4, 3, "g"))
+    data, tries = permtest.gen_random_network_data(seed_G, n_tries=50, rng=np.random.default_rng(5))
+    G = data["G"]
+    assert sorted(G.nodes()) == sorted(seed_G.nodes()) == data["nodes"] and tries >= 1
+    assert min(d for _, d in G.degree()) >= 2
+    D_ref = oracle.regularized_laplacian(G, data["nodes"], 0.05)
+    assert oracle.rel_max_err(data["D"], D_ref) < 1e-11
+    assert oracle.rel_max_err(data["C"] @ data["C"].T, D_ref) < 1e-11
+    res = permtest.run_permutation_test(seed_G, seed_G, [(n, n) for n in data["nodes"][:40]], 10,
+                                        n_permutations=3, mode="graphs", seed=1)
+    assert res["errs"] == 0 and len(res["random"]["mean_diffs"]) == 3

@@ -222,15 +222,19 @@ def test_c3_full_size_properties(m):
     inp = pipeline.graph_inputs(G1, G2, homs, k)
     assert len(inp["source_nodes"]) == n1 and len(inp["target_nodes"]) == n2
     emb = pipeline.embed_device(n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"])
-    W1, W2, P = emb.W1[:, :n1], emb.W2[:, :n2], emb.P[:, :n2]
+    W1, P = emb.W1[:, :n1], emb.P[:, :n2]
     S = emb.scores()[:, :n2]
     ones1 = torch.ones(n1, dtype=torch.float64, device=W1.device)
     L1 = torch.tril(W1)
     assert float((L1.t() @ (L1 @ ones1) - 1).abs().max()) < 1e-12        # D1 1 = 1
     ls = torch.tensor([a for a, _ in inp["landmark_idxs"]], device=W1.device)
     lt = torch.tensor([b for _, b in inp["landmark_idxs"]], device=W1.device)
-    L2 = torch.tril(W2)
-    D2_rows = L2[:, lt].t() @ L2                                          # D2[Lt,:]
+    C2 = torch.tril(emb.L2[:, :n2])                                       # Cholesky factor of A2
+    E = torch.zeros(n2, len(lt), dtype=torch.float64, device=W1.device)
+    E[lt, torch.arange(len(lt), device=W1.device)] = 1
+    D2_rows = torch.cholesky_solve(E, C2).t().contiguous()               # D2[Lt,:]
+    A2 = emb.dev.assemble(n2, inp["edges2"][0], inp["edges2"][1], 0.05)[:, :n2]
+    assert float((D2_rows @ A2 - E.t()).abs().max()) < 1e-12              # rows of A2^-1
     assert float((S[ls, :] - D2_rows).abs().max() / D2_rows.abs().max()) < 1e-11
     # residual of the source factor on sampled rows: rows of (W1 A1) must be unit vectors
     A1 = emb.dev.assemble(n1, inp["edges1"][0], inp["edges1"][1], 0.05)[:, :n1]

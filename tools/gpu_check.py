@@ -256,7 +256,7 @@ def _():
 @section("timing")
 def _():
     out = {}
-    for n in (4096, 8192, 16384):
+    for n in ((4096, 8192, 16384) if not os.environ.get("QUICK") else ()):
         a = torch.randn(n, n, dtype=torch.float64, device=dev)
         b = torch.randn(n, n, dtype=torch.float64, device=dev)
         c = torch.empty(n, n, dtype=torch.float64, device=dev)
@@ -268,7 +268,7 @@ def _():
         out["cublas_%d" % n] = 2 * n ** 3 / best / 1e9
         print("  cublas n=%d: %.2f ms %.2f TF" % (n, best, out["cublas_%d" % n]), flush=True)
         del a, b, c
-    for n in (2048, 4096, 8192, 16000, 20000):
+    for n in (128, 256, 512, 1024, 2048, 4096, 8192, 16000, 20000):
         A0 = spd(n, 1)
         A = torch.empty_like(A0)
         linv = torch.empty(lib.munk_linv_bytes(n) // 8, dtype=torch.float64, device=dev)
