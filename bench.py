@@ -159,6 +159,27 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """Reserve the real stdout for the one JSON line: everything else that writes to fd 1
+    (NCCL's version banner, library chatter) is redirected to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -168,6 +189,7 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        _quiet_stdout()       # NCCL prints its version banner on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from munk_b200 import pipeline
@@ -176,6 +198,8 @@ def run_gpu(args):
     import ctypes
 
     dev = Device(local)
+    if world > 1 and args.mode == "strong":
+        return run_gpu_dist(args, dev, rank, world, local)
     n1, n2, k, inp, graphs = make_inputs(args.config, rank)
     fl = pipeline_flops(n1, n2, k)
     tdev = dev.torch_device
@@ -346,13 +370,139 @@ def run_gpu(args):
                                     "sample": desc, "host": info}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def run_gpu_dist(args, dev, rank, world, local):
+    """N > 1: ONE graph pair of the configuration, the pipeline sharded over the ranks
+    (munk_b200/dist.py: block-column-cyclic Cholesky with NCCL panel broadcasts, per-rank column
+    solves, row-sharded score product).  Strong scaling: total work is fixed."""
+    import ctypes
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from munk_b200 import dist as mdist
+    from munk_b200._lib import lib
+
+    n1, n2, k, inp, _ = make_inputs(args.config, 0)            # same graph pair on every rank
+    fl = pipeline_flops(n1, n2, k)
+    tdev = dev.torch_device
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    e1 = (dev.ints(inp["edges1"][0]), dev.ints(inp["edges1"][1]))
+    e2 = (dev.ints(inp["edges2"][0]), dev.ints(inp["edges2"][1]))
+    phase_ms = {}
+
+    def step(edges1, edges2, record=False):
+        marks = [] if record else None
+        out = mdist.dist_embed_scores(dev, n1, edges1, n2, edges2, inp["landmark_idxs"], rank, world,
+                                      marks=marks)
+        if record:
+            torch.cuda.current_stream().synchronize()
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                phase_ms.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(e1, e2)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    dev.stats(reset=True)
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        out = step(e1, e2, record=True)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    launches, counted_flops = dev.stats(reset=True)
+    clocks = sampler.stop()
+
+    # e2e: host edge arrays in, every rank's shard of C1 and S (and P on rank 0) out to pinned memory
+    m_own = len(out["rows"])
+    h_e1 = [torch.from_numpy(x).pin_memory() for x in inp["edges1"]]
+    h_e2 = [torch.from_numpy(x).pin_memory() for x in inp["edges2"]]
+    out_C1 = torch.empty((m_own, n1), dtype=torch.float64, pin_memory=True)
+    out_S = torch.empty((m_own, n2), dtype=torch.float64, pin_memory=True)
+    out_P = torch.empty((n1, n2), dtype=torch.float64, pin_memory=True) if rank == 0 else None
+    h2d = sum(t.numel() * t.element_size() for t in h_e1 + h_e2)
+    d2h = out_C1.numel() * 8 + out_S.numel() * 8 + (out_P.numel() * 8 if out_P is not None else 0)
+
+    def e2e_step():
+        d1 = [t.to(tdev, non_blocking=True) for t in h_e1]
+        d2 = [t.to(tdev, non_blocking=True) for t in h_e2]
+        o = step(d1, d2)
+        out_C1.copy_(o["C1"], non_blocking=True)
+        out_S.copy_(o["S"][:, :n2], non_blocking=True)
+        if out_P is not None:
+            out_P.copy_(o["P"][:, :n2], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    q0, q1 = ev(), ev()
+    q0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    q1.record()
+    barrier()
+    e2e_ms = q0.elapsed_time(q1)
+
+    t = torch.tensor([ms, e2e_ms, float(h2d), float(d2h), float(launches)], dtype=torch.float64, device=tdev)
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = float(tmax[0]), float(tmax[1])
+    if rank == 0:
+        ms_step = ms / args.steps
+        value = fl["total"] / (ms_step * 1e-3) / 1e12
+        e2e_val = fl["total"] / (e2e_ms / e2e_steps * 1e-3) / 1e12
+        v = ctypes.c_double()
+        lib.munk_microbench_dmma(local, 20000, ctypes.byref(v)); dmma_peak = v.value
+        med = {kk: statistics.median(vv) for kk, vv in phase_ms.items()}
+        rows0 = len(mdist.ColumnCyclic(n1, world).rows_of(0))
+        # rank 0's score launch: its rows x n2, k >= first row of each 128-row tile
+        r0 = np.asarray(mdist.ColumnCyclic(n1, world).rows_of(0))
+        score_flops0 = float(sum(2.0 * n2 * (n1 - (int(r) // 128) * 128) for r in r0))
+        achieved = score_flops0 / (med["score"] * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: source %d / target %d nodes, %d landmarks, lam 0.05, Barabasi-Albert m=10 "
+                                   "(seeds 1/2), ONE graph pair sharded over %d GPUs" % (args.config, n1, n2, k, world),
+                       "parallelism": "1 x %d block-column-cyclic Cholesky (NCCL panel broadcasts), per-rank column "
+                                      "solves, row-sharded score product" % world,
+                       "l2": "inputs larger than L2: %.1f GB of FP64 matrices per step vs 126 MB L2" % (
+                           (n1 * n1 + n2 * n2 + 2 * n1 * n2) * 8 / 1e9),
+                       "useful_tflop_per_step": fl["total"] / 1e12, "seconds_per_pipeline": ms_step * 1e-3},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(tsum[2]), "d2h_bytes_per_step": int(tsum[3]),
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                    "note": "edge arrays H2D on every rank; each rank's rows of C1 and S (and C2hat^T on rank 0) D2H into pinned memory"},
+            "gpu_launches": int(tsum[4]),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
+                         "frac": achieved / dmma_peak, "traffic": None,
+                         "kernel": "dgemm_dmma_tma_kernel<MC,MC> score launch on rank 0: %d rows of S = X_own^T P "
+                                   "(staircase k-range, %.2f TFLOP)" % (rows0, score_flops0 / 1e12),
+                         "peak_source": "measured in this run on rank 0: FP64 DMMA issue-rate microbenchmark"},
+            "phases": {kk: {"ms": vv} for kk, vv in med.items()},
+            "cpu_baseline": None,
+        }
+        emit(line)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="strong", choices=["strong", "replicas"],
+                    help="N>1: shard one pipeline over the GPUs (strong) or one graph pair per GPU (replicas)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)

@@ -86,7 +86,22 @@ int munk_trtri(munk_workspace_t* ws, int n, double* L, long ld, double* linv, vo
  * is target_D[:, target_idxs] (munk/munk/munk.py:110) without forming the full inverse.
  */
 int munk_trsm_left(munk_workspace_t* ws, int n, const double* L, long ld, const double* linv,
-                   int transposed, int nrhs, double* B, long ldb, void* stream);
+                   int transposed, int nrhs, double* B, long ldb, const int* stair, void* stream);
+/* `stair` (device int array, one entry per 128 columns of B, or NULL; forward solve only): the
+ * first row at which that column tile of B is non-zero.  Work above it is skipped, so solving
+ * for a set of columns of L^-1 (B = columns of the identity) costs only their non-zero part. */
+
+/* B (m x s, in place) <- B L^-T: the panel solve of the blocked Cholesky (multi-GPU driver). */
+int munk_trsm_right(munk_workspace_t* ws, int m, double* B, long ldb, const double* L, long ldl,
+                    int s, const double* linv, void* stream);
+
+/* munk_dgemm with staircase operands: stair_m[t] / stair_n[t] (device, per 128-wide tile, or NULL)
+ * give the first global k at which the A-operand rows of m-tile t / the B-operand rows of n-tile
+ * t are non-zero; row0 and k0 are the global indices of C's row 0 and of k = 0. */
+int munk_dgemm_stair(munk_workspace_t* ws, int a_layout, int b_layout, int M, int N, int K,
+                     double alpha, const double* A, long lda, const double* B, long ldb, double beta,
+                     double* C, long ldc, int flags, const int* stair_m, const int* stair_n,
+                     int row0, int k0, void* stream);
 
 /* out (cols x rows) = in (rows x cols)^T, row-major. */
 int munk_transpose(int rows, int cols, const double* in, long ldi, double* out, long ldo,

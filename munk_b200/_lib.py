@@ -28,7 +28,12 @@ SIGNATURES = {
     "munk_trtri": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p]),
     "munk_gram_lower": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p]),
     "munk_trsm_left": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_int, c_int, c_void_p,
-                               c_long, c_void_p]),
+                               c_long, c_void_p, c_void_p]),
+    "munk_trsm_right": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_long, c_int, c_void_p,
+                                c_void_p]),
+    "munk_dgemm_stair": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_double, c_void_p,
+                                 c_long, c_void_p, c_long, c_double, c_void_p, c_long, c_int,
+                                 c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "munk_transpose": (c_int, [c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p]),
     "munk_dgemm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long,
                            c_void_p, c_long, c_double, c_void_p, c_long, c_int, c_void_p]),

@@ -112,13 +112,38 @@ int munk_trtri(munk_workspace_t* ws, int n, double* L, long ld, double* linv, vo
 }
 
 int munk_trsm_left(munk_workspace_t* ws, int n, const double* L, long ld, const double* linv,
-                   int transposed, int nrhs, double* B, long ldb, void* stream) {
+                   int transposed, int nrhs, double* B, long ldb, const int* stair, void* stream) {
   if (!ws) return -1;
   if (n < 0) return -2;
   if (ld < n || (ld & 1)) return -4;
   if (nrhs < 0) return -7;
   if (ldb < nrhs || (ldb & 1)) return -9;
-  return trsm_left(ws, n, L, ld, linv, transposed, nrhs, B, ldb, S(stream));
+  return trsm_left(ws, n, L, ld, linv, transposed, nrhs, B, ldb, stair, S(stream));
+}
+
+int munk_trsm_right(munk_workspace_t* ws, int m, double* B, long ldb, const double* L, long ldl,
+                    int s, const double* linv, void* stream) {
+  if (!ws) return -1;
+  if (m < 0 || s < 0) return -2;
+  if (ldb < s || (ldb & 1) || ldl < s || (ldl & 1)) return -4;
+  return trsm_right(ws, m, B, ldb, L, ldl, s, linv, S(stream));
+}
+
+int munk_dgemm_stair(munk_workspace_t* ws, int a_layout, int b_layout, int M, int N, int K,
+                     double alpha, const double* A, long lda, const double* B, long ldb, double beta,
+                     double* C, long ldc, int flags, const int* stair_m, const int* stair_n,
+                     int row0, int k0, void* stream) {
+  if (!ws) return -1;
+  if ((a_layout | b_layout) & ~1) return -2;
+  if (M < 0 || N < 0 || K < 0) return -4;
+  GemmDesc g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.a_layout = a_layout;
+  g.B = B; g.ldb = ldb; g.b_layout = b_layout;
+  g.C = C; g.ldc = ldc;
+  g.alpha = alpha; g.beta = beta; g.flags = flags;
+  g.stair_m = stair_m; g.stair_n = stair_n; g.stair_row0 = row0; g.stair_k0 = k0;
+  return gemm_launch(ws, g, S(stream));
 }
 
 int munk_transpose(int rows, int cols, const double* in, long ldi, double* out, long ldo,

@@ -44,6 +44,9 @@ struct KernelArgs {
   long ws_slice;
   long ws_ld;
   int mt, nt, gn;   // tile grid and rasterisation strip width (in tiles)
+  const int* stair_n;   // see GemmDesc
+  const int* stair_m;
+  int stair_row0, stair_k0;
 };
 
 // k index (0..15 inside a stage) read by lane-quad position j = lane & 3 at sub-step s:
@@ -100,6 +103,12 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
   if (g.flags & GF_KLO_N) klo = max(klo, n0);
   if (g.flags & GF_KHI_M) khi = min(khi, m0 + BM);
   if (g.flags & GF_KHI_N) khi = min(khi, n0 + BN);
+  if (g.stair_n) {
+    const int first = g.stair_n[tile_n];
+    if (g.stair_row0 + m0 + BM <= first) return;        // whole tile above the staircase: stays zero
+    klo = max(klo, first - g.stair_k0);
+  }
+  if (g.stair_m) klo = max(klo, g.stair_m[tile_m] - g.stair_k0);
   int it_lo = klo / BK;
   int it_hi = (khi + BK - 1) / BK;
   if (it_hi < it_lo) it_hi = it_lo;
@@ -251,6 +260,7 @@ __global__ void splitk_reduce_kernel(const KernelArgs g) {
   const int row = blockIdx.y;
   if (col >= g.N) return;
   if ((g.flags & GF_TILE_LOWER) && (col / BN) * BN >= (row / BM) * BM + BM) return;
+  if (g.stair_n && g.stair_row0 + (row / BM) * BM + BM <= g.stair_n[col / BN]) return;
   const bool pair = col + 1 < g.N;
   double s0 = 0.0, s1 = 0.0;
   for (int z = 0; z < g.nsplit; ++z) {
@@ -393,6 +403,8 @@ int gemm_launch(Workspace* ws, const GemmDesc& g, cudaStream_t stream, int scrat
   ka.C = g.C; ka.ldc = g.ldc;
   ka.alpha = g.alpha; ka.beta = g.beta;
   ka.flags = g.flags;
+  ka.stair_n = g.stair_n; ka.stair_m = g.stair_m;
+  ka.stair_row0 = g.stair_row0; ka.stair_k0 = g.stair_k0;
   ka.nsplit = 1; ka.ws = nullptr; ka.ws_slice = 0; ka.ws_ld = 0;
 
   // Split-K whenever the tile grid cannot fill the 148 SMs: one 128x128 tile advances only 16 of

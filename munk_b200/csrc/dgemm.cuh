@@ -25,6 +25,14 @@ struct GemmDesc {
   double* C; long ldc;                      // row-major M x N
   double alpha, beta;
   int flags;
+  // Optional "staircase" structure (device arrays, one int per 128-wide tile, nullptr = off).
+  // stair_n[t]: the columns of n-tile t (of the B operand / of C) are zero for global rows
+  //   < stair_n[t]: tiles with stair_row0 + m0 + 128 <= stair_n[t] are skipped and k starts at
+  //   stair_n[t] - stair_k0.   stair_m[t]: same for the A operand of m-tile t (k-range only).
+  const int* stair_n;
+  const int* stair_m;
+  int stair_row0;   // global row index of C's row 0
+  int stair_k0;     // global index of k = 0
 };
 
 struct Workspace;  // api.cu

@@ -54,6 +54,7 @@ struct Rec {
   cudaStream_t stream;
   double* linv;      // leaf inverses of this matrix, block g at linv + g*128*128
   int scratch;       // split-K buffer of `stream` (0 caller's stream, 1 side stream)
+  const int* stair = nullptr;   // forward left solve: first non-zero row of each 128-column RHS tile
 };
 
 int leaf_potrf(Rec& r, double* A, long ld, int nb, int gidx) {
@@ -212,6 +213,7 @@ int trsm_left_rec(Rec& r, const double* L, long ldl, int n, double* B, long ldb,
     g.B = B; g.ldb = ldb; g.b_layout = OP_MC;
     g.C = B; g.ldc = ldb;
     g.alpha = 1.0; g.beta = 0.0; g.flags = transposed ? GF_KLO_M : GF_KHI_M;
+    if (!transposed && r.stair) { g.stair_n = r.stair; g.stair_row0 = gidx; g.stair_k0 = gidx; }
     return gemm_launch(r.ws, g, r.stream, r.scratch);
   }
   const int n1 = split_point(n), n2 = n - n1;
@@ -225,6 +227,7 @@ int trsm_left_rec(Rec& r, const double* L, long ldl, int n, double* B, long ldb,
   if (!transposed) {
     MUNK_TRY(trsm_left_rec(r, L, ldl, n1, B, ldb, nrhs, gidx, false));
     g.M = n2; g.K = n1; g.a_layout = OP_KC; g.B = B; g.C = B2;          // B2 -= L21 X1
+    if (r.stair) { g.stair_n = r.stair; g.stair_row0 = gidx + n1; g.stair_k0 = gidx; }
     MUNK_TRY(gemm_launch(r.ws, g, r.stream, r.scratch));
     return trsm_left_rec(r, L22, ldl, n2, B2, ldb, nrhs, gidx + n1, false);
   }
@@ -237,10 +240,18 @@ int trsm_left_rec(Rec& r, const double* L, long ldl, int n, double* B, long ldb,
 }  // namespace
 
 int trsm_left(Workspace* ws, int n, const double* L, long ld, const double* linv, int transposed,
-              int nrhs, double* B, long ldb, cudaStream_t stream) {
+              int nrhs, double* B, long ldb, const int* stair, cudaStream_t stream) {
   if (n <= 0 || nrhs <= 0) return MUNK_OK;
   Rec r{ws, stream, const_cast<double*>(linv), 0};
+  r.stair = transposed ? nullptr : stair;
   return trsm_left_rec(r, L, ld, n, B, ldb, nrhs, 0, transposed != 0);
+}
+
+int trsm_right(Workspace* ws, int m, double* B, long ldb, const double* L, long ldl, int s,
+               const double* linv, cudaStream_t stream) {
+  if (m <= 0 || s <= 0) return MUNK_OK;
+  Rec r{ws, stream, const_cast<double*>(linv), 0};
+  return trsm_rec(r, B, ldb, m, L, ldl, s, 0);
 }
 
 size_t linv_bytes_for(int n) { return (size_t)((n + LEAF - 1) / LEAF) * LEAF * LEAF * 8; }

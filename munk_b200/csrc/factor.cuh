@@ -20,7 +20,13 @@ int trtri_lower(Workspace* ws, int n, double* L, long ld, double* linv, cudaStre
 
 // B (n x nrhs, row-major, in place) <- L^-1 B (transposed = 0) or L^-T B (transposed = 1), with
 // the factor and leaf inverses left by potrf_lower.
+// `stair` (device, optional, forward solve only): one int per 128 columns of B = first row where
+// that column tile is non-zero (multiple of 128 not required); work above it is skipped.
 int trsm_left(Workspace* ws, int n, const double* L, long ld, const double* linv, int transposed,
-              int nrhs, double* B, long ldb, cudaStream_t stream);
+              int nrhs, double* B, long ldb, const int* stair, cudaStream_t stream);
+
+// B (m x s, in place) <- B L^-T with the s x s factor L and its leaf inverses.
+int trsm_right(Workspace* ws, int m, double* B, long ldb, const double* L, long ldl, int s,
+               const double* linv, cudaStream_t stream);
 
 }  // namespace munk

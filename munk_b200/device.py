@@ -215,11 +215,27 @@ class Device:
         self.gemm(KC, MC, n1, n2, kq, 1.0, Q1, Z, 0.0, P, 0)           # P = M^T Z
         return P
 
-    def trsm_left(self, L, n, linv, B, nrhs, transposed):
-        """B[:n, :nrhs] <- L^-1 B or L^-T B in place (factor + leaf inverses from potrf)."""
+    def trsm_left(self, L, n, linv, B, nrhs, transposed, stair=None):
+        """B[:n, :nrhs] <- L^-1 B or L^-T B in place (factor + leaf inverses from potrf).
+        `stair`: int32 CUDA tensor, first non-zero row of every 128-column tile of B (forward only)."""
         check(lib.munk_trsm_left(self._ws, n, _ptr(L), L.stride(0), _ptr(linv), 1 if transposed else 0,
-                                 nrhs, _ptr(B), B.stride(0), self.stream()), "munk_trsm_left")
+                                 nrhs, _ptr(B), B.stride(0), _ptr(stair) if stair is not None else None,
+                                 self.stream()), "munk_trsm_left")
         return B
+
+    def trsm_right(self, B, m, L, s, linv):
+        """B[:m, :s] <- B L^-T in place (panel solve)."""
+        check(lib.munk_trsm_right(self._ws, m, _ptr(B), B.stride(0), _ptr(L), L.stride(0), s, _ptr(linv),
+                                  self.stream()), "munk_trsm_right")
+        return B
+
+    def gemm_stair(self, a_layout, b_layout, M, N, K, alpha, A, B, beta, C, flags=0, stair_m=None,
+                   stair_n=None, row0=0, k0=0):
+        check(lib.munk_dgemm_stair(self._ws, a_layout, b_layout, M, N, K, alpha, _ptr(A), A.stride(0),
+                                   _ptr(B), B.stride(0), beta, _ptr(C), C.stride(0), flags,
+                                   _ptr(stair_m) if stair_m is not None else None,
+                                   _ptr(stair_n) if stair_n is not None else None, row0, k0,
+                                   self.stream()), "munk_dgemm_stair")
 
     def transpose(self, X, rows, cols):
         out = self.empty(cols, rows)

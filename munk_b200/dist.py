@@ -1,0 +1,374 @@
+"""Multi-GPU MUNK pipeline: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch).
+
+Process grid.  The factorisations use a 1 x P block-column-cyclic layout (block width 512): block
+column j belongs to rank j mod P.  With NVSwitch every rank sees every peer at full bandwidth, so
+the per-rank panel traffic of a P_r x P_c grid (the whole panel, n^2/2 doubles in total) is the
+same for any grid shape; 1 x P keeps each panel's factorisation on one GPU (no intra-panel
+exchange) and leaves every rank with the complete factor L, which is what the later stages want:
+
+  potrf   right-looking; the owner of panel j+1 applies panel j to it first (look-ahead), factors
+          it (diagonal block + panel solve, munk_potrf / munk_trsm_right) and broadcasts it
+          (ncclBroadcast, asynchronous) while all ranks apply panel j to the block columns they
+          own (DMMA syrk).  At the end every rank holds all of L and the leaf inverses.
+  W, Q1   columns of W = L^-1 are independent given L: each rank solves L X = E for the identity
+          columns of its own blocks and (redundantly, k columns) for the landmark columns, in ONE
+          forward solve whose right-hand side is a staircase (munk_trsm_left with `stair`), so
+          only the non-zero part of every column is computed: n^3/(3P) flops per rank, no exchange.
+  C1, S   rank r owns the rows of C1 = W^T and of S = C1 C2hat^T that belong to its blocks
+          (row-block sharding): S_r = X_r^T P with the same staircase on the k-range.
+          P = C2hat^T is small work (2 n1 n2 k flops) and is formed on every rank from the
+          replicated Q1 and D2[Lt,:], so the score product needs no all-gather.
+  stats   separate_scores means: per-rank partial sums + one 4-scalar all-reduce.
+  perms   permutation test: munk_b200/permtest.py (round-robin, one all-gather of 3 doubles each).
+
+The driver is written against a small `ops` object so that the schedule, the ownership map and the
+packing can be exercised on CPU tensors with gloo (tests/test_dist_cpu.py supplies a torch-CPU
+`ops`); the product always uses CudaOps (no CPU fallback: CudaOps needs a Device).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .device import KC, MC, TILE_LOWER, pad16, landmark_groups
+
+NB = 512
+
+
+class ColumnCyclic:
+    """Ownership map of a 1 x P block-column-cyclic layout."""
+
+    def __init__(self, n, world, nb=NB):
+        self.n, self.world, self.nb = int(n), int(world), int(nb)
+        self.nblk = (self.n + self.nb - 1) // self.nb
+
+    def owner(self, j):
+        return j % self.world
+
+    def cols(self, j):
+        return j * self.nb, min(self.n, (j + 1) * self.nb)
+
+    def blocks_of(self, rank):
+        return list(range(rank, self.nblk, self.world))
+
+    def rows_of(self, rank):
+        """Global row indices (of C1 / S) owned by `rank`, ascending."""
+        out = []
+        for j in self.blocks_of(rank):
+            a, b = self.cols(j)
+            out.extend(range(a, b))
+        return out
+
+
+class CudaOps:
+    """The four operations of the distributed Cholesky on a munk_b200 Device."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.device = dev.torch_device
+
+    def syrk_lower(self, C, X, Y, m, nc, k):
+        """C[:m, :nc] -= X[:m, :k] Y[:nc, :k]^T (at least the tiles touching the lower triangle)."""
+        self.dev.gemm(KC, KC, m, nc, k, -1.0, X, Y, 1.0, C, TILE_LOWER)
+
+    def factor_panel(self, A, n, c0, w, linv):
+        """In place: Cholesky of the w x w diagonal block at (c0, c0) and the panel solve below."""
+        diag = A[c0:, c0:]
+        lv = linv[(c0 // 128) * 128 * 128:]
+        self.dev.potrf(diag, w, linv=lv, check_info=False)
+        below = n - (c0 + w)
+        if below > 0:
+            self.dev.trsm_right(A[c0 + w:, c0:], below, diag, w, lv)
+
+    def info(self):
+        return self.dev.potrf_info()
+
+
+def _panel_elems(n, c0, w):
+    ldp = pad16(w)
+    return (n - c0) * ldp, ldp, ((w + 127) // 128) * 128 * 128
+
+
+def dist_potrf_steps(ops, A, n, linv, rank, world, group=None, nb=NB, stream=None):
+    """Generator form of dist_potrf: enqueues one panel step per next() (on `stream` if given),
+    so that two independent factorisations can be interleaved from one host thread and overlap
+    on the device (each is latency-bound in its panel chain)."""
+    import contextlib
+    ctx = (lambda: torch.cuda.stream(stream)) if stream is not None else contextlib.nullcontext
+    cc = ColumnCyclic(n, world, nb)
+    max_elems = n * pad16(min(nb, n)) + ((min(nb, n) + 127) // 128) * 128 * 128
+    with ctx():
+        bufs = [torch.empty(max_elems, dtype=torch.float64, device=A.device) for _ in range(2)]
+
+    def pack(j, buf):
+        c0, c1 = cc.cols(j)
+        w = c1 - c0
+        ne, ldp, nl = _panel_elems(n, c0, w)
+        view = buf[:ne].view(n - c0, ldp)
+        view[:, :w].copy_(A[c0:, c0:c1])
+        if ldp != w:
+            view[:, w:].zero_()
+        lo = (c0 // 128) * 128 * 128
+        buf[ne:ne + nl].copy_(linv[lo:lo + nl])
+
+    def unpack(j, buf):
+        c0, c1 = cc.cols(j)
+        w = c1 - c0
+        ne, ldp, nl = _panel_elems(n, c0, w)
+        A[c0:, c0:c1].copy_(buf[:ne].view(n - c0, ldp)[:, :w])
+        lo = (c0 // 128) * 128 * 128
+        linv[lo:lo + nl].copy_(buf[ne:ne + nl])
+
+    def bcast(j, buf, async_op):
+        c0, c1 = cc.cols(j)
+        ne, _, nl = _panel_elems(n, c0, c1 - c0)
+        if world == 1:
+            return None
+        return dist.broadcast(buf[:ne + nl], src=_global_rank(group, cc.owner(j)), group=group,
+                              async_op=async_op)
+
+    cur, nxt = bufs
+    with ctx():
+        if rank == cc.owner(0):
+            ops.factor_panel(A, n, 0, cc.cols(0)[1], linv)
+            pack(0, cur)
+        bcast(0, cur, async_op=False)
+        if rank != cc.owner(0):
+            unpack(0, cur)
+    yield
+
+    for j in range(cc.nblk):
+        with ctx():
+            c0, c1 = cc.cols(j)
+            w = c1 - c0
+            ne, ldp, _ = _panel_elems(n, c0, w)
+            pan = cur[:ne].view(n - c0, ldp)                     # panel j, rows c0.., on every rank
+            work = None
+            if j + 1 < cc.nblk:
+                r1, r1e = cc.cols(j + 1)
+                w1 = r1e - r1
+                if rank == cc.owner(j + 1):                      # look-ahead: update, factor, send
+                    ops.syrk_lower(A[r1:, r1:], pan[r1 - c0:], pan[r1 - c0:], n - r1, w1, w)
+                    ops.factor_panel(A, n, r1, w1, linv)
+                    pack(j + 1, nxt)
+                work = bcast(j + 1, nxt, async_op=True)
+            for c in cc.blocks_of(rank):                         # my other trailing block columns
+                if c <= j + 1:
+                    continue
+                cs, ce = cc.cols(c)
+                ops.syrk_lower(A[cs:, cs:], pan[cs - c0:], pan[cs - c0:], n - cs, ce - cs, w)
+            if j + 1 < cc.nblk:
+                if work is not None:
+                    work.wait()
+                if rank != cc.owner(j + 1):
+                    unpack(j + 1, nxt)
+            cur, nxt = nxt, cur
+        yield
+
+
+def dist_potrf(ops, A, n, linv, rank, world, group=None, nb=NB, check=True):
+    """Distributed in-place Cholesky of the (replicated-storage) matrix A; on return every rank
+    holds the complete factor in the lower triangle of A and all leaf inverses in `linv`.
+    Returns the non-SPD flag (max over ranks; 0 = ok), or None with check=False."""
+    for _ in dist_potrf_steps(ops, A, n, linv, rank, world, group, nb):
+        pass
+    if not check:
+        return None          # the caller collects the flag later (keeps the host running ahead)
+    return dist_potrf_flag(ops, A.device, world, group)
+
+
+def dist_potrf_flag(ops, device, world, group=None):
+    """Synchronises, then max over ranks of the non-SPD flag of `ops` (0 = ok)."""
+    flag = torch.tensor([ops.info()], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return int(flag.item())
+
+
+_SIDE = {}
+
+
+def _side_resources(dev, world, group):
+    """(second Device/workspace, second stream, second communicator) of this process for work
+    that runs concurrently with the main chain; created once.  Collective on first call when
+    world > 1 (dist.new_group)."""
+    key = (dev.index, id(group))
+    res = _SIDE.get(key)
+    if res is None:
+        from .device import Device
+        group2 = None
+        if world > 1:
+            ranks = list(range(world)) if group is None else dist.get_process_group_ranks(group)
+            group2 = dist.new_group(ranks=ranks)
+        res = _SIDE[key] = (Device(dev.index), torch.cuda.Stream(device=dev.index), group2)
+    return res
+
+
+def _global_rank(group, group_rank):
+    if group is None:
+        return group_rank
+    return dist.get_global_rank(group, group_rank)
+
+
+# ---------------------------------------------------------------------------------------------
+def staircase_rhs(n, owned_cols, landmark_cols, device):
+    """One-hot right-hand side [E_owned | E_landmarks] (n x ncols, zero padded to 128-column
+    tiles) and its staircase: the first non-zero row of each 128-column tile.
+
+    owned_cols: ascending global column indices owned by this rank (whole blocks);
+    landmark_cols: ascending distinct landmark indices.  Returns (X, stair, n_owned_padded)."""
+    own = np.asarray(owned_cols, dtype=np.int64)
+    lm = np.asarray(landmark_cols, dtype=np.int64)
+    n_own_pad = (len(own) + 127) // 128 * 128
+    n_lm_pad = (len(lm) + 127) // 128 * 128
+    ncols = n_own_pad + n_lm_pad
+    X = torch.zeros((n, max(ncols, 2)), dtype=torch.float64, device=device)
+    col_of = np.concatenate([np.arange(len(own)), n_own_pad + np.arange(len(lm))])
+    row_of = np.concatenate([own, lm])
+    if len(row_of):
+        X[torch.as_tensor(row_of, device=device), torch.as_tensor(col_of, device=device)] = 1.0
+    stair = np.full(ncols // 128, n, dtype=np.int32)           # empty tile: nothing to do
+    for t in range(ncols // 128):
+        rows = row_of[(col_of >= 128 * t) & (col_of < 128 * (t + 1))]
+        if len(rows):
+            stair[t] = int(rows.min())
+    return X, torch.from_numpy(stair).to(device), n_own_pad
+
+
+def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, group=None,
+                      src_lam=0.05, tgt_lam=0.05, homolog_idxs=None, marks=None):
+    """The whole hot path on `world` GPUs.  Returns a dict with the rank's shard:
+       rows   global row indices of C1 / S owned by this rank
+       C1     (len(rows), n1) rows of the source embedding       (CUDA tensor)
+       P      (n1, n2) C2hat^T, replicated                        (CUDA tensor, padded ld)
+       S      (len(rows), n2) rows of the score matrix            (CUDA tensor)
+       stats  (hom_mean, other_mean, diff) over the full matrix if homolog_idxs is given."""
+    ops = CudaOps(dev)
+
+    def mark(name):
+        if marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
+    mark("start")
+    s_idx = [int(a) for a, _ in landmark_idxs]
+    t_idx = [int(b) for _, b in landmark_idxs]
+    # distinct source landmarks in ascending order; groups of target rows to average per landmark
+    uniq_first, gptr_f, members_f = landmark_groups(s_idx)
+    order = np.argsort(np.asarray(uniq_first, dtype=np.int64), kind="stable")
+    uniq = [uniq_first[g] for g in order]
+    gptr, members = [0], []
+    for g in order:
+        members.extend(members_f[gptr_f[g]:gptr_f[g + 1]])
+        gptr.append(len(members))
+
+    # 1. factors, replicated on every rank.  The target chain (assembly, Cholesky, the k-column
+    #    solve for D2[Lt,:]) is independent of the source chain and, like it, latency-bound in its
+    #    panel steps, so it runs concurrently: own stream, own workspace, own communicator.
+    main = torch.cuda.current_stream(dev.index)
+    dev2, side, group2 = _side_resources(dev, world, group)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        A2 = dev2.assemble(n2, edges2[0], edges2[1], tgt_lam)
+        linv2 = dev2.new_linv(n2)
+        ops2 = CudaOps(dev2)
+    A1 = dev.assemble(n1, edges1[0], edges1[1], src_lam)
+    linv1 = dev.new_linv(n1)
+    # interleave the two panel loops step by step (one host thread feeds both streams)
+    src_steps = dist_potrf_steps(ops, A1, n1, linv1, rank, world, group)
+    tgt_steps = dist_potrf_steps(ops2, A2, n2, linv2, rank, world, group2, stream=side)
+    src_live = tgt_live = True
+    while src_live or tgt_live:
+        if src_live:
+            src_live = next(src_steps, "done") != "done"
+        if tgt_live:
+            tgt_live = next(tgt_steps, "done") != "done"
+    with torch.cuda.stream(side):
+        B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
+    mark("potrf_src")
+    # 2. my columns of W1 and the landmark columns Q1, one staircase solve
+    cc = ColumnCyclic(n1, world)
+    rows = cc.rows_of(rank)
+    X, stair, n_own_pad = staircase_rhs(n1, rows, uniq, dev.torch_device)
+    ncols = X.shape[1]
+    if ncols >= 128:
+        dev.trsm_left(A1, n1, linv1, X, ncols, transposed=False, stair=stair)
+    kq = len(uniq)
+    Q1 = X[:, n_own_pad:]                                        # n1 x pad128(k'), view
+
+    mark("solve_src")
+    # 3. projection (replicated): join the target chain, check both factorisations
+    main.wait_stream(side)
+    for t in (A2, linv2, B):
+        t.record_stream(main)
+    bad = max(dist_potrf_flag(ops, dev.torch_device, world, group),
+              dist_potrf_flag(ops2, dev.torch_device, world, group))
+    if bad:
+        from .device import NotPositiveDefinite
+        raise NotPositiveDefinite("matrix is not positive definite (pivot %d)" % (bad - 1))
+    P = dev.project(Q1, n1, B, n2, (gptr, members))
+
+    mark("embed")
+    # 4. my rows of S = C1 C2hat^T:  S_r = X_own^T P, k-range clipped by the same staircase
+    m_own = len(rows)
+    S = dev.empty(max(m_own, 1), n2)
+    if m_own:
+        dev.gemm_stair(MC, MC, m_own, n2, n1, 1.0, X, P, 0.0, S, 0, stair_m=stair, k0=0)
+    C1 = X[:, :m_own].t() if m_own else X[:, :0].t()            # (m_own, n1) view of the solve
+
+    mark("score")
+    out = dict(rows=rows, C1=C1, P=P, S=S[:m_own], n1=n1, n2=n2)
+    if homolog_idxs is not None:
+        out["stats"] = dist_score_means(dev, S, rows, n1, n2, landmark_idxs, homolog_idxs, world, group)
+    return out
+
+
+def dist_score_means(dev, S_local, rows, n1, n2, landmark_idxs, homolog_idxs, world, group=None):
+    """mean(H_H), mean(other), difference over the row-sharded score matrix: local partial sums
+    (munk_separate_scores_means on the local rows) + one all-reduce of 4 doubles."""
+    sums = torch.zeros(4, dtype=torch.float64, device=dev.torch_device)
+    if rows:
+        plan = _local_plan(len(rows), n2, rows, landmark_idxs, homolog_idxs)
+        out = plan.means(dev, S_local)
+        torch.cuda.current_stream(dev.index).synchronize()
+        o = out.cpu().numpy()
+        hh_sum = o[0] * o[3] if o[3] > 0 else 0.0
+        ot_sum = o[1] * o[4] if o[4] > 0 else 0.0
+        sums = torch.tensor([hh_sum, o[3], ot_sum, o[4]], dtype=torch.float64, device=dev.torch_device)
+    if world > 1:
+        dist.all_reduce(sums, group=group)
+    s = sums.cpu().numpy()
+    hom_mean, other_mean = s[0] / s[1], s[2] / s[3]
+    return hom_mean, other_mean, hom_mean - other_mean
+
+
+def _local_plan(m_local, n2, rows, landmark_idxs, homolog_idxs):
+    """SeparatePlan of the local row block: row flags / cell lists restricted to owned rows,
+    column flags from every landmark."""
+    from .scores_plan import SeparatePlan
+    local_of = {g: i for i, g in enumerate(rows)}
+    plan = SeparatePlan.__new__(SeparatePlan)
+    ls = np.array([a for a, _ in landmark_idxs], dtype=np.int64)
+    lt = np.array([b for _, b in landmark_idxs], dtype=np.int64)
+    hs = np.array([a for a, _ in homolog_idxs], dtype=np.int64)
+    ht = np.array([b for _, b in homolog_idxs], dtype=np.int64)
+    rowL = np.zeros(m_local, dtype=np.uint8)
+    for a in ls:
+        if int(a) in local_of:
+            rowL[local_of[int(a)]] = 1
+    colL = np.zeros(n2, dtype=np.uint8)
+    colL[lt] = 1
+    pair_keys = set(zip(ls.tolist(), lt.tolist()))
+    cells = sorted({(local_of[a], b) for a, b in zip(hs.tolist(), ht.tolist())
+                    if a in local_of and (a, b) not in pair_keys})
+    h_row = np.array([c[0] for c in cells], dtype=np.int32)
+    h_col = np.array([c[1] for c in cells], dtype=np.int32)
+    n_nonl_rows = int(m_local - rowL.sum())
+    n_nonl_cols = int(n2 - colL.sum())
+    in_other = sum(1 for r, c in cells if not rowL[r] and not colL[c])
+    plan.n1, plan.n2 = m_local, n2
+    plan.rowL, plan.colL = rowL, colL
+    plan.h_row, plan.h_col = h_row, h_col
+    plan.n_hh = len(cells)
+    plan.n_other = n_nonl_rows * n_nonl_cols - in_other
+    return plan

@@ -68,3 +68,49 @@ def test_statistics_match_reference_formulae():
     idx = [(i, i + 1) for i in range(20)]
     a, b = permuted_homolog_idxs(idx, 3), permuted_homolog_idxs(idx, 3)
     assert a == b and sorted(a) == idx and a != permuted_homolog_idxs(idx, 4)
+
+
+def test_column_cyclic_map():
+    from munk_b200.dist import ColumnCyclic
+    cc = ColumnCyclic(2000, 3, nb=512)
+    assert cc.nblk == 4 and cc.cols(3) == (1536, 2000)
+    assert [cc.owner(j) for j in range(4)] == [0, 1, 2, 0]
+    assert cc.blocks_of(0) == [0, 3] and cc.blocks_of(2) == [2]
+    rows = sorted(sum((cc.rows_of(r) for r in range(3)), []))
+    assert rows == list(range(2000))
+    assert cc.rows_of(0) == list(range(512)) + list(range(1536, 2000))
+
+
+def test_staircase_rhs_layout():
+    from munk_b200.dist import staircase_rhs
+    import torch
+    X, stair, n_own_pad = staircase_rhs(1000, list(range(512, 700)), [3, 600, 999], torch.device("cpu"))
+    assert n_own_pad == 256 and X.shape == (1000, 384)
+    assert stair.tolist() == [512, 640, 3]
+    assert X.sum() == 188 + 3 and X[512, 0] == 1 and X[699, 187] == 1 and X[600, 257] == 1
+    assert X[:, 188:256].abs().sum() == 0
+
+
+def test_distributed_cholesky_schedule_two_ranks_gloo():
+    """dist_potrf on 2 gloo ranks with the torch-CPU ops: every rank must end with the complete
+    factor of the same SPD matrix (look-ahead order, packing and broadcasts are exercised;
+    block width 96 gives 5 block columns incl. a ragged one)."""
+    outs = run_ranks("""
+        sys.path.insert(0, os.path.join(%r, "tests"))
+        from cpu_ops import TorchCpuOps
+        from munk_b200.dist import dist_potrf
+        n = 430
+        g = torch.Generator().manual_seed(7)
+        X = torch.randn(n, n, dtype=torch.float64, generator=g)
+        A0 = X @ X.t() / n + 2 * torch.eye(n, dtype=torch.float64)
+        A = torch.zeros(n, 432, dtype=torch.float64)
+        A[:, :n] = A0
+        linv = torch.zeros(((n + 127) // 128) * 128 * 128, dtype=torch.float64)
+        bad = dist_potrf(TorchCpuOps(), A, n, linv, rank, world, nb=96)
+        L = torch.tril(A[:, :n])
+        err = float((L - torch.linalg.cholesky(A0)).abs().max())
+        print(bad, err)
+    """ % ROOT)
+    for o in outs:
+        bad, err = o.split()
+        assert int(bad) == 0 and float(err) < 1e-12

@@ -163,6 +163,45 @@ def test_permutation_unit_and_experiment(dev):
     assert abs(res["effect_size"] - oracle.effect_size(want[0], np.array(diffs))) < 1e-6 * abs(res["effect_size"])
 
 
+def test_distributed_driver_single_rank_matches_oracle(dev):
+    """munk_b200.dist with world = 1 (same code path as N ranks, minus the broadcasts): panel
+    driver, staircase solve for the W columns + landmark columns, staircase score product, means."""
+    from munk_b200 import dist as mdist, pipeline, synthetic
+    G1, G2, homs = synthetic.make_case(1300, 700, 4, 90, seeds=(41, 42))
+    homs = homs[:7] + [(homs[3][0], homs[50][1])] + homs[7:]            # one repeated source landmark
+    k = 40
+    ref = oracle.embed_networks(G1, G2, homs, k)
+    S_ref = oracle.scores(ref["C1"], ref["C2"])
+    inp = pipeline.graph_inputs(G1, G2, homs, k)
+    out = mdist.dist_embed_scores(dev, 1300, inp["edges1"], 700, inp["edges2"], inp["landmark_idxs"],
+                                  rank=0, world=1, homolog_idxs=ref["homolog_idxs"])
+    assert out["rows"] == list(range(1300))
+    assert oracle.rel_max_err(out["S"][:, :700].cpu().numpy(), S_ref) < 1e-10
+    C1 = out["C1"].cpu().numpy()
+    assert oracle.rel_max_err(C1 @ C1.T, ref["D1"]) < 1e-11
+    want = oracle.difference_in_means(ref["C1"], ref["D2"], ref["homolog_idxs"], k)
+    got = out["stats"]
+    assert np.allclose([got[2], got[1], got[0]], want, rtol=1e-9, atol=0)
+
+
+def test_staircase_solve_matches_dense(dev):
+    import torch
+    from munk_b200.dist import staircase_rhs
+    n = 1100
+    A0 = spd(n, 3)
+    A = dev.empty(n, n)
+    A[:, :n] = A0
+    linv = dev.potrf(A, n)
+    own = list(range(512, 900))
+    lms = [0, 5, 300, 777, 1099]
+    X, stair, n_own_pad = staircase_rhs(n, own, lms, dev.torch_device)
+    dev.trsm_left(A, n, linv, X, X.shape[1], transposed=False, stair=stair)
+    W = torch.linalg.inv(torch.linalg.cholesky(A0))
+    assert relerr(X[:, :len(own)], W[:, own]) < 1e-11
+    assert relerr(X[:, n_own_pad:n_own_pad + len(lms)], W[:, lms]) < 1e-11
+    assert float(X[:, len(own):n_own_pad].abs().max()) == 0.0
+
+
 def test_random_network_generator(dev):
     """gen_random_network_data (gen_random_network.py:78-84): same nodes and degrees as the seed
     graph, D and C consistent with the oracle on the generated graph."""
