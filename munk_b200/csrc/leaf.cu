@@ -73,9 +73,10 @@ potrf_leaf_kernel(double* __restrict__ A, long lda, int nb, double* __restrict__
       for (int j = 0; j < PW; ++j) {
         const double d = __shfl_sync(FULL, a[j], j);
         if (!(d > 0.0) && !bad) bad = c0 + j + 1;
-        const double s = sqrt(d);
-        const double rinv = 1.0 / s;
-        a[j] = (lane == j) ? s : a[j] * rinv;
+        // one reciprocal square root instead of sqrt + divide on the serial chain
+        // (rsqrt is <= 1 ulp; L[j][j] = d * rsqrt(d) is then within 2 ulp of sqrt(d))
+        const double rinv = rsqrt(d);
+        a[j] = (lane == j) ? d * rinv : a[j] * rinv;
 #pragma unroll
         for (int t = j + 1; t < PW; ++t) {
           const double l = __shfl_sync(FULL, a[j], t);      // L[c0+t][c0+j]

@@ -297,6 +297,21 @@ def landmark_groups(source_idx):
     return uniq, gptr, members
 
 
+_side = {}
+
+
+def side_device(dev):
+    """(second Device, high-priority CUDA stream) on the same GPU, for running two independent
+    chains of work concurrently (own workspace, so split-K scratch, look-ahead stream and status
+    flag are not shared).  The block scheduler serves streams by priority, then age: the chain on
+    the high-priority stream keeps its speed, the other one fills the SMs it leaves idle.
+    Created once per device."""
+    res = _side.get(dev.index)
+    if res is None:
+        res = _side[dev.index] = (Device(dev.index), torch.cuda.Stream(device=dev.index, priority=-1))
+    return res
+
+
 _default = {}
 
 

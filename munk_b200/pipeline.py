@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import util
-from .device import default_device, landmark_groups
+from .device import NotPositiveDefinite, default_device, landmark_groups, side_device
 
 
 class PhaseTimer:
@@ -71,7 +71,7 @@ class DeviceEmbedding:
 
 
 def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.05, dev=None,
-                 keep_target_factor=True):
+                 keep_target_factor=True, overlap=True):
     """Hot path on index data: edges as (u, v) int32 arrays in sorted-node order, landmark_idxs
     as [(source_row, target_row)].  Returns a DeviceEmbedding."""
     dev = dev or default_device()
@@ -80,18 +80,53 @@ def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.
     t_idx = [int(b) for _, b in landmark_idxs]
     uniq, gptr, members = landmark_groups(s_idx)
 
-    with timer("source_regularized_laplacian_runtime"):
-        A1 = dev.assemble(n1, edges1[0], edges1[1], src_lam)
-        linv1 = dev.potrf(A1, n1)
-    with timer("source_rkhs_factorization_runtime"):
-        W1 = dev.trtri(A1, n1, linv1)
+    # The target chain (assembly, Cholesky, k-column solve for D2[Lt,:]) does not depend on the
+    # source chain; both are partly latency-bound, so the target runs on a second stream and
+    # workspace and fills the gaps.  Its timer is then the time the main stream still has to wait
+    # for it after the source phases ("exposed" time); with overlap=False the phases are serial
+    # and the four timers mean exactly what the reference's do (munk.py:134-164).
+    main = torch.cuda.current_stream(dev.index)
+    if overlap:
+        # source chain first and on the high-priority stream; the target chain, enqueued behind
+        # it on the caller's stream with a second workspace, runs in the SMs the source leaves idle
+        dev2, hi = side_device(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        hi.wait_stream(main)
+        with torch.cuda.stream(hi):
+            ev[0].record()
+            A1 = dev.assemble(n1, edges1[0], edges1[1], src_lam)
+            linv1 = dev.potrf(A1, n1, check_info=False)
+            ev[1].record()
+            W1 = dev.trtri(A1, n1, linv1)
+            ev[2].record()
+        A2 = dev2.assemble(n2, edges2[0], edges2[1], tgt_lam)
+        linv2 = dev2.potrf(A2, n2, check_info=False)
+        B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
+        hi.synchronize()
+        timer.times["source_regularized_laplacian_runtime"] = ev[0].elapsed_time(ev[1]) * 1e-3
+        timer.times["source_rkhs_factorization_runtime"] = ev[1].elapsed_time(ev[2]) * 1e-3
+        with timer("target_regularized_laplacian_runtime"):      # what is left of it after the source
+            main.wait_stream(hi)
+            for t in (A1, linv1):
+                t.record_stream(main)
+            with torch.cuda.stream(hi):
+                bad1 = dev.potrf_info()
+            if bad1 or dev2.potrf_info():
+                raise NotPositiveDefinite("%s matrix is not positive definite" % ("source" if bad1 else "target"))
         del linv1
-    with timer("target_regularized_laplacian_runtime"):
-        A2 = dev.assemble(n2, edges2[0], edges2[1], tgt_lam)
-        linv2 = dev.potrf(A2, n2)
+    else:
+        with timer("source_regularized_laplacian_runtime"):
+            A1 = dev.assemble(n1, edges1[0], edges1[1], src_lam)
+            linv1 = dev.potrf(A1, n1)
+        with timer("source_rkhs_factorization_runtime"):
+            W1 = dev.trtri(A1, n1, linv1)
+            del linv1
+        with timer("target_regularized_laplacian_runtime"):
+            A2 = dev.assemble(n2, edges2[0], edges2[1], tgt_lam)
+            linv2 = dev.potrf(A2, n2)
+            B = dev.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
     with timer("embed_runtime"):
         Q1 = dev.gather_cols_lower(W1, n1, uniq)
-        B = dev.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
         P = dev.project(Q1, n1, B, n2, (gptr, members))
         dev.raise_if_not_spd()
     return DeviceEmbedding(dev, n1, n2, W1, A2 if keep_target_factor else None, P, timer.times)
