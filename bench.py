@@ -292,22 +292,17 @@ def run_gpu(args):
     h_e1 = [torch.from_numpy(x).pin_memory() for x in inp["edges1"]]
     h_e2 = [torch.from_numpy(x).pin_memory() for x in inp["edges2"]]
     import numpy as np
-    h_u = torch.from_numpy(np.asarray(uniq, dtype=np.int32)).pin_memory()
-    h_t = torch.from_numpy(np.asarray(t_idx, dtype=np.int32)).pin_memory()
-    out_C1 = torch.empty((n1, n1), dtype=torch.float64, pin_memory=True)
-    out_P = torch.empty((n1, n2), dtype=torch.float64, pin_memory=True)
-    out_S = torch.empty((n1, n2), dtype=torch.float64, pin_memory=True)
-    h2d = sum(t.numel() * t.element_size() for t in h_e1 + h_e2 + [h_u, h_t])
-    d2h = sum(t.numel() * t.element_size() for t in (out_C1, out_P, out_S))
+    # The public device API (what scripts/compute_embeddings.py calls): host edge/index arrays in,
+    # C1, C2hat^T and S streamed to the pinned buffers of a HostSink while later stages compute.
+    sink = pipeline.HostSink(dev, n1, n2)
+    h2d = sum(t.numel() * t.element_size() for t in h_e1 + h_e2) + 8 * len(t_idx)
+    d2h = sum(t.numel() * t.element_size() for t in (sink.C1, sink.P, sink.S))
 
     def e2e_step():
-        d_e1 = [t.to(tdev, non_blocking=True) for t in h_e1]
-        d_e2 = [t.to(tdev, non_blocking=True) for t in h_e2]
-        P = step(d_e1, d_e2, h_u.to(tdev, non_blocking=True), h_t.to(tdev, non_blocking=True))
-        C1 = dev.transpose_lower(A1, n1)
-        out_C1.copy_(C1[:, :n1], non_blocking=True)
-        out_P.copy_(P[:, :n2], non_blocking=True)
-        out_S.copy_(S_buf[:, :n2], non_blocking=True)
+        emb = pipeline.embed_device(n1, h_e1, n2, h_e2, inp["landmark_idxs"], dev=dev,
+                                    keep_target_factor=False, sink=sink)
+        emb.scores_streamed(sink)
+        sink.wait()
         torch.cuda.current_stream().synchronize()
 
     e2e_step()

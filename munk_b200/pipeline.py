@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import util
-from .device import NotPositiveDefinite, default_device, landmark_groups, side_device
+from .device import MC, NotPositiveDefinite, default_device, landmark_groups, side_device
 
 
 class PhaseTimer:
@@ -43,6 +43,80 @@ class _Phase:
         return False
 
 
+class HostSink:
+    """Pinned host buffers for the three results of the pipeline — C1 (n1 x n1), P = C2hat^T
+    (n1 x n2), S (n1 x n2) — and a copy stream.  Each result is copied out as soon as it exists,
+    so the device-to-host traffic (8.3 GB at 20k/16k nodes) overlaps the remaining compute
+    instead of following it (reference: the arrays scripts/compute_embeddings.py:72-85 pickles).
+    Reusable across calls; allocate once (pinning host memory is slow)."""
+
+    def __init__(self, dev, n1, n2, pinned=True, prefault_threads=8):
+        """pinned=True: page-locked buffers, asynchronous copies (pinning 8.3 GB costs seconds —
+        measured 2.5 s per 3.2 GB on the B200 hosts — so do it once and reuse the sink).
+        pinned=False (one-shot callers such as the CLI): pageable buffers whose pages are touched
+        by background threads while the GPU computes; the copies happen in wait()."""
+        self.pinned = pinned
+        opts = dict(dtype=torch.float64, pin_memory=pinned)
+        self.C1 = torch.empty((n1, n1), **opts)
+        self.P = torch.empty((n1, n2), **opts)
+        self.S = torch.empty((n1, n2), **opts)
+        self.dev = dev
+        self.stream = torch.cuda.Stream(device=dev.index)
+        self._pending, self._threads = [], []
+        if not pinned and prefault_threads > 0:
+            import threading
+            flat = [t.view(-1) for t in (self.C1, self.P, self.S)]
+            chunks = []
+            for f in flat:
+                step = max(1, (f.numel() + prefault_threads - 1) // prefault_threads)
+                chunks.extend(f[i:i + step] for i in range(0, f.numel(), step))
+
+            def touch(parts):
+                for p in parts:
+                    p.zero_()              # first touch: the kernel maps and zeroes the pages
+
+            for w in range(prefault_threads):
+                th = threading.Thread(target=touch, args=(chunks[w::prefault_threads],), daemon=True)
+                th.start()
+                self._threads.append(th)
+
+    def push(self, dst, src):
+        """dst (host) <- src (CUDA tensor, ready on the current stream)."""
+        if not self.pinned:
+            self._pending.append((dst, src))
+            return
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev.index))
+        with torch.cuda.stream(self.stream):
+            dst.copy_(src, non_blocking=True)
+        src.record_stream(self.stream)
+
+    def push_source_factor(self, W1, n1):
+        """C1 = W1^T: transpose on the copy stream, then out."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev.index))
+        with torch.cuda.stream(self.stream):
+            C = self.dev.transpose_lower(W1, n1, ld=n1 + (n1 & 1))
+            if self.pinned:
+                self.C1.copy_(C[:, :n1], non_blocking=True)
+            else:
+                self._pending.append((self.C1, C[:, :n1]))
+        W1.record_stream(self.stream)
+
+    def wait(self):
+        for th in self._threads:
+            th.join()
+        self._threads = []
+        torch.cuda.current_stream(self.dev.index).synchronize()
+        self.stream.synchronize()
+        for dst, src in self._pending:
+            dst.copy_(src)
+        self._pending = []
+
+    def arrays(self):
+        """(C1, C2hat, S) as numpy arrays over the pinned buffers; C2hat is the transposed view the
+        reference returns (munk.py:109-110)."""
+        return self.C1.numpy(), self.P.numpy().T, self.S.numpy()
+
+
 class DeviceEmbedding:
     """Result of embed_device(): everything still on the GPU."""
 
@@ -56,6 +130,25 @@ class DeviceEmbedding:
         if self._S is None:
             self._S = self.dev.score(self.W1, self.n1, self.P, self.n2)
         return self._S
+
+    def scores_streamed(self, sink, row_blocks=4):
+        """S = W1^T P in `row_blocks` row blocks (each one DMMA launch; the k-range of a block
+        starts at its first row, so the triangular saving is kept); every finished block is
+        copied to sink.S on the copy stream while the next one is computed."""
+        dev, n1, n2 = self.dev, self.n1, self.n2
+        S = dev.empty(n1, n2)
+        tiles = (n1 + 127) // 128
+        per = (tiles + row_blocks - 1) // row_blocks
+        for b in range(row_blocks):
+            r0, r1 = min(n1, b * per * 128), min(n1, (b + 1) * per * 128)
+            if r1 <= r0:
+                continue
+            stair = dev.ints([r0 + 128 * t for t in range((r1 - r0 + 127) // 128)])
+            dev.gemm_stair(MC, MC, r1 - r0, n2, n1, 1.0, self.W1[:, r0:], self.P, 0.0, S[r0:], 0,
+                           stair_m=stair, k0=0)
+            sink.push(sink.S[r0:r1], S[r0:r1, :n2])
+        self._S = S
+        return S
 
     # host copies (API edge)
     def source_C(self):
@@ -71,7 +164,7 @@ class DeviceEmbedding:
 
 
 def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.05, dev=None,
-                 keep_target_factor=True, overlap=True):
+                 keep_target_factor=True, overlap=True, sink=None):
     """Hot path on index data: edges as (u, v) int32 arrays in sorted-node order, landmark_idxs
     as [(source_row, target_row)].  Returns a DeviceEmbedding."""
     dev = dev or default_device()
@@ -125,10 +218,14 @@ def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.
             A2 = dev.assemble(n2, edges2[0], edges2[1], tgt_lam)
             linv2 = dev.potrf(A2, n2)
             B = dev.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
+    if sink is not None:
+        sink.push_source_factor(W1, n1)          # C1 leaves while the projection and scores run
     with timer("embed_runtime"):
         Q1 = dev.gather_cols_lower(W1, n1, uniq)
         P = dev.project(Q1, n1, B, n2, (gptr, members))
         dev.raise_if_not_spd()
+    if sink is not None:
+        sink.push(sink.P, P[:, :n2])
     return DeviceEmbedding(dev, n1, n2, W1, A2 if keep_target_factor else None, P, timer.times)
 
 
@@ -148,18 +245,24 @@ def graph_inputs(source_G, target_G, homologs, n_landmarks):
                 landmark_homs=landmark_homs, landmark_idxs=landmark_idxs, edges1=edges1, edges2=edges2)
 
 
-def embed_and_score(source_G, target_G, homologs, n_landmarks, src_lam=0.05, tgt_lam=0.05, dev=None):
-    """Everything the CLI needs in one device-resident pass.
+def embed_and_score(source_G, target_G, homologs, n_landmarks, src_lam=0.05, tgt_lam=0.05, dev=None,
+                    sink=None):
+    """Everything the CLI needs in one device-resident pass, results streamed to pinned host
+    memory while the remaining stages run (pass a reusable HostSink to avoid re-pinning).
 
     Returns dict(source_X, target_X, scores, source_nodes, target_nodes, landmarks, runtimes).
     """
+    dev = dev or default_device()
     inp = graph_inputs(source_G, target_G, homologs, n_landmarks)
-    emb = embed_device(len(inp["source_nodes"]), inp["edges1"], len(inp["target_nodes"]), inp["edges2"],
-                       inp["landmark_idxs"], src_lam, tgt_lam, dev=dev, keep_target_factor=False)
+    n1, n2 = len(inp["source_nodes"]), len(inp["target_nodes"])
+    sink = sink or HostSink(dev, n1, n2, pinned=False)
+    emb = embed_device(n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"], src_lam, tgt_lam,
+                       dev=dev, keep_target_factor=False, sink=sink)
     t0 = time.time()
-    S = emb.scores_host()
-    runtimes = dict(emb.runtimes)
+    emb.scores_streamed(sink)
+    sink.wait()
     score_time = time.time() - t0
-    return dict(source_X=emb.source_C(), target_X=emb.target_C_hat(), scores=S,
+    source_X, target_X, S = sink.arrays()
+    return dict(source_X=source_X, target_X=target_X, scores=S,
                 source_nodes=inp["source_nodes"], target_nodes=inp["target_nodes"],
-                landmarks=inp["landmark_homs"], runtimes=runtimes, score_runtime=score_time)
+                landmarks=inp["landmark_homs"], runtimes=dict(emb.runtimes), score_runtime=score_time)

@@ -163,6 +163,23 @@ def test_permutation_unit_and_experiment(dev):
     assert abs(res["effect_size"] - oracle.effect_size(want[0], np.array(diffs))) < 1e-6 * abs(res["effect_size"])
 
 
+def test_streamed_outputs_equal_direct_outputs(dev):
+    """HostSink path (results copied out on a second stream while later stages run, scores in
+    row blocks) gives the same arrays as the plain serial device path (to rounding: the row-block
+    launches pick different split-K factors, i.e. a different summation order)."""
+    from munk_b200 import pipeline, synthetic
+    G1, G2, homs = synthetic.make_case(1500, 900, 4, 80, seeds=(51, 52))
+    res = pipeline.embed_and_score(G1, G2, homs, 30)
+    inp = pipeline.graph_inputs(G1, G2, homs, 30)
+    emb = pipeline.embed_device(1500, inp["edges1"], 900, inp["edges2"], inp["landmark_idxs"], overlap=False)
+    assert oracle.rel_max_err(res["scores"], emb.scores_host()) < 1e-13
+    assert oracle.rel_max_err(res["source_X"], emb.source_C()) < 1e-13
+    assert oracle.rel_max_err(res["target_X"], emb.target_C_hat()) < 1e-13
+    assert res["target_X"].shape == (900, 1500) and res["target_X"].flags.f_contiguous
+    ref = oracle.embed_networks(G1, G2, homs, 30)
+    assert oracle.rel_max_err(res["scores"], oracle.scores(ref["C1"], ref["C2"])) < 1e-11
+
+
 def test_distributed_driver_single_rank_matches_oracle(dev):
     """munk_b200.dist with world = 1 (same code path as N ranks, minus the broadcasts): panel
     driver, staircase solve for the W columns + landmark columns, staircase score product, means."""
