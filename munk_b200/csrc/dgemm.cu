@@ -166,6 +166,15 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+    } else if (g.beta != 0.0 && g.nsplit == 1) {
+      // The other 31 lanes pull this tile of C into L2 while the main loop runs.  Without it the
+      // CTAs of a wave (which run in lockstep) all miss to DRAM in their epilogues at the same
+      // moment: ~19 MB in and ~19 MB out in one burst, 8.5 us per tile with the tensor pipe idle
+      // (tools/syrk_probe.py: K = 512 update at 28 TFLOP/s with beta = 1 vs 31 with beta = 0).
+      for (int idx = lane - 1; idx < BM * (BN / 16); idx += 31) {
+        const int r = m0 + idx / (BN / 16), c = n0 + (idx % (BN / 16)) * 16;
+        if (r < g.M && c < g.N) prefetch_l2(g.C + (long)r * g.ldc + c);
+      }
     }
     return;
   }
@@ -223,6 +232,31 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
   const double beta = split ? 0.0 : g.beta;
   const bool mirror = !split && (g.flags & GF_SYM_MIRROR) && (n0 + BN <= m0);
 
+  // beta != 0: bring the old C tile into the (now idle) pipeline shared memory with cp.async —
+  // 32 independent 16-byte copies per thread, one round trip to L2 (the producer warp prefetched
+  // the tile there) — instead of 32 dependent load -> fma -> store round trips per lane, which is
+  // what the compiler emits for a read-modify-write through one pointer (~10 us per tile).
+  // Row stride 1088 B keeps the 128-bit fragment reads below bank-conflict-free.
+  constexpr int CS = BN * 8 + 64;
+  if (beta != 0.0) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // every consumer warp is done with the ring
+    const int tid = threadIdx.x;                         // 0..255 (consumer warps only)
+#pragma unroll 4
+    for (int i = 0; i < (BM * BN / 2) / 256; ++i) {
+      const int q = i * 256 + tid;                       // 16-byte chunk of the tile
+      const int rl = q >> 6, cl = (q & 63) * 2;
+      const int row = m0 + rl, col = n0 + cl;
+      const uint32_t dst = tiles_u32 + rl * CS + cl * 8;
+      const double* src = out + (long)row * ldo + col;
+      if (row < g.M && col + 1 < g.N)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      else if (row < g.M && col < g.N)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+  }
+
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     const int row = m0 + wm + 8 * t + r8;
@@ -234,9 +268,10 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
       double v0 = alpha * acc[t][u][0];
       double v1 = alpha * acc[t][u][1];
       double* p = out + (long)row * ldo + col;
+      const double* sp = reinterpret_cast<const double*>(tiles + (wm + 8 * t + r8) * CS + (wn + 8 * u + 2 * j) * 8);
       if (col + 1 < g.N) {
         if (beta != 0.0) {
-          const double2 old = *reinterpret_cast<const double2*>(p);
+          const double2 old = *reinterpret_cast<const double2*>(sp);
           v0 += beta * old.x;
           v1 += beta * old.y;
         }
@@ -246,7 +281,7 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
           g.C[(long)(col + 1) * g.ldc + row] = v1;
         }
       } else {
-        if (beta != 0.0) v0 += beta * p[0];
+        if (beta != 0.0) v0 += beta * sp[0];
         p[0] = v0;
         if (mirror) g.C[(long)col * g.ldc + row] = v0;
       }

@@ -25,13 +25,16 @@
 #include "workspace.cuh"
 
 #include <algorithm>
+#include <vector>
 
 namespace munk {
 
 namespace {
 
 constexpr int LEAF = MUNK_LEAF;
-constexpr int PANEL = 512;          // block-column width of the look-ahead driver
+constexpr int PANEL = 512;          // block-column width of the look-ahead driver ...
+constexpr int PANEL_SMALL = 256;    // ... once fewer than PANEL_SWITCH columns remain
+constexpr int PANEL_SWITCH = 8192;
 
 // dst (nb x nb block inside a row-major matrix) <- src (128-ld leaf inverse)
 __global__ void copy_leaf_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ src,
@@ -120,7 +123,18 @@ int potrf_rec(Rec& r, double* A, long ld, int n, int gidx) {
 //     main stream : wait panel[j];  columns beyond block column j+1 -= panel j contributions
 //                   (one lower-tile DMMA syrk, K = w);  record upd[j]
 int potrf_lookahead(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t main) {
-  const int nblk = (n + PANEL - 1) / PANEL;
+  // Panel boundaries: 512 columns while the trailing matrix is large (each 128x128 tile of the
+  // trailing syrk then runs 32 k-iterations and amortises its prologue/epilogue), 256 columns
+  // once it is small, where the panel chain on the side stream is the critical path and a
+  // shorter chain (and shorter main-stream tiles to wait behind) matters more.  Measured on
+  // B200: n = 8192 13.3 -> 12.3 ms with 256 throughout, n = 20000 107 -> 127 ms.
+  std::vector<int> start;
+  for (int c = 0; c < n;) {
+    start.push_back(c);
+    c += (n - c > PANEL_SWITCH) ? PANEL : PANEL_SMALL;
+  }
+  start.push_back(n);
+  const int nblk = (int)start.size() - 1;
   MUNK_TRY(ws->ensure_side(2 * (size_t)nblk + 2));
   MUNK_TRY(ws->ensure_splitk(0, SPLITK_RESERVE));
   MUNK_TRY(ws->ensure_splitk(1, SPLITK_RESERVE));
@@ -140,31 +154,62 @@ int potrf_lookahead(Workspace* ws, int n, double* A, long ld, double* linv, cuda
 
   MUNK_CUDA_TRY(cudaEventRecord(fork_ev, main));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(side, fork_ev, 0));
-  MUNK_TRY(factor_panel(0, std::min(PANEL, n)));
+  MUNK_TRY(factor_panel(0, start[1]));
   MUNK_CUDA_TRY(cudaEventRecord(panel_ev[0], side));
+
+  // MUNK_TRACE_POTRF=1: per-step device timeline (diagnostics only; synchronises at the end)
+  const bool trace = getenv("MUNK_TRACE_POTRF") != nullptr;
+  std::vector<cudaEvent_t> tm0, tm1, ts0, ts1, ts2;
+  auto tick = [&](std::vector<cudaEvent_t>& v, cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    v.push_back(e);
+  };
 
   int last_panel = 0;
   for (int j = 0; j + 1 < nblk; ++j) {
-    const int c0 = j * PANEL, w = PANEL;              // every panel but the last is full width
+    const int c0 = start[j], w = start[j + 1] - c0;
     const int r1 = c0 + w;                            // first row/column of block column j+1
-    const int w1 = std::min(PANEL, n - r1);
+    const int w1 = start[j + 2] - r1;
     const int r2 = r1 + w1;                           // first column the main stream updates
     const double* pan = A + (long)r1 * ld + c0;       // panel j rows >= r1
     // side: look-ahead update of block column j+1, then its factorisation
     if (j > 0) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, upd_ev[j - 1], 0));
+    tick(ts0, side);
     MUNK_TRY(syrk_update(rs, A + (long)r1 * ld + r1, ld, n - r1, w1, pan, pan, ld, w));
+    tick(ts1, side);
     MUNK_TRY(factor_panel(r1, w1));
+    tick(ts2, side);
     MUNK_CUDA_TRY(cudaEventRecord(panel_ev[j + 1], side));
     last_panel = j + 1;
     // main: the rest of the trailing matrix
     MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[j], 0));
+    tick(tm0, main);
     if (r2 < n) {
       const double* pan2 = A + (long)r2 * ld + c0;    // panel j rows >= r2
       MUNK_TRY(syrk_update(rm, A + (long)r2 * ld + r2, ld, n - r2, n - r2, pan2, pan2, ld, w));
     }
+    tick(tm1, main);
     MUNK_CUDA_TRY(cudaEventRecord(upd_ev[j], main));
   }
   MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[last_panel], 0));   // join
+  if (trace) {
+    cudaStreamSynchronize(main);
+    fprintf(stderr, "potrf_lookahead n=%d: step rem | main: start dur | side: start lookahead panel (ms)\n", n);
+    for (size_t j = 0; j < tm0.size(); ++j) {
+      float a = 0, b = 0, c = 0, d = 0, e = 0;
+      cudaEventElapsedTime(&a, tm0[0], tm0[j]);
+      cudaEventElapsedTime(&b, tm0[j], tm1[j]);
+      cudaEventElapsedTime(&c, tm0[0], ts0[j]);
+      cudaEventElapsedTime(&d, ts0[j], ts1[j]);
+      cudaEventElapsedTime(&e, ts1[j], ts2[j]);
+      fprintf(stderr, "  %3zu %6d | %8.3f %7.3f | %8.3f %7.3f %7.3f\n", j, n - start[j + 1], a, b, c, d, e);
+    }
+    for (auto* v : {&tm0, &tm1, &ts0, &ts1, &ts2})
+      for (cudaEvent_t ev : *v) cudaEventDestroy(ev);
+  }
   return MUNK_OK;
 }
 
