@@ -165,6 +165,28 @@ int munk_separate_scores_means(int n1, int n2, const double* S, long lds,
                                const int* h_row, const int* h_col, double n_other,
                                double* rowsum_scratch, double* out5, void* stream);
 
+/*
+ * out[p] = X[r[p], 0:k] . Z[0:k, c[p]]: single scores S[r,c] of the factored form S = X Z
+ * (X = D1[:,Ls] n1 x k, Z = D1[Ls,Ls]^-1 D2[Lt,:] k x n2) without forming S.  Used by the opt-in
+ * rank-k permutation statistic, never by the dense path.
+ */
+int munk_pair_dots(int npairs, const int* r, const int* c, int k, const double* X, long ldx,
+                   const double* Z, long ldz, double* out, void* stream);
+
+/*
+ * Z (k x n) = pinv(G) B for a symmetric positive semi-definite k x k matrix G (overwritten):
+ * one-sided Jacobi eigen-decomposition on the device, eigenvalues <= max(rcond^2, 4 k eps) *
+ * lambda_max truncated; *rank_host receives the retained rank.  Synchronises `stream`.
+ * `work` holds munk_sym_pinv_work_bytes(k, n) bytes.  Rank-revealing fallback for
+ * np.linalg.pinv(source_C[source_idxs,:]) (munk/munk/munk.py:109) when the landmark Gram matrix
+ * is not safely positive definite; G = M M^T squares the singular values of M, so singular
+ * values of M below ~sqrt(4 k eps) sigma_max count as zero (numpy's cut is 1e-15 sigma_max).
+ */
+int munk_sym_pinv_solve(munk_workspace_t* ws, int k, double* G, long ldg, int n, const double* B,
+                        long ldb, double* Z, long ldz, double* work, double rcond, int* rank_host,
+                        void* stream);
+size_t munk_sym_pinv_work_bytes(int k, int n);
+
 /* Micro-benchmarks used by bench.py / tools to measure the FP64 ceilings of the box.
  * Each runs on `device`, blocks, and returns TFLOP/s in *tflops. */
 int munk_microbench_dmma(int device, int iters, double* tflops);

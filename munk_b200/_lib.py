@@ -48,6 +48,11 @@ SIGNATURES = {
     "munk_separate_scores_means": (c_int, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_int,
                                            c_void_p, c_void_p, c_double, c_void_p, c_void_p,
                                            c_void_p]),
+    "munk_pair_dots": (c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_long, c_void_p, c_long,
+                               c_void_p, c_void_p]),
+    "munk_sym_pinv_solve": (c_int, [c_void_p, c_int, c_void_p, c_long, c_int, c_void_p, c_long, c_void_p,
+                                    c_long, c_void_p, c_double, _P(c_int), c_void_p]),
+    "munk_sym_pinv_work_bytes": (c_size_t, [c_int, c_int]),
     "munk_microbench_dmma": (c_int, [c_int, c_int, _P(c_double)]),
     "munk_microbench_dfma": (c_int, [c_int, c_int, _P(c_double)]),
 }

@@ -9,7 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libmunk_b200.so")
-SOURCES = ["api.cu", "dgemm.cu", "factor.cu", "leaf.cu", "assemble.cu", "scores.cu", "microbench.cu"]
+SOURCES = ["api.cu", "dgemm.cu", "factor.cu", "leaf.cu", "assemble.cu", "scores.cu", "jacobi.cu",
+           "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

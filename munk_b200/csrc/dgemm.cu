@@ -28,7 +28,8 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int STAGES = 6;
 constexpr int CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int GEMM_THREADS = CONSUMER_WARPS * 32;   // thread 0 doubles as the TMA producer
+constexpr int LOOKAHEAD = 4;                        // stages in flight ahead of the consumers
 constexpr int TILE_BYTES = BM * BK * 8;         // 16 KB
 constexpr int STAGE_BYTES = 2 * TILE_BYTES;     // A + B
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
@@ -138,48 +139,61 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
   }
   __syncthreads();
 
-  if (warp == CONSUMER_WARPS) {
-    // ---------------- producer: one lane issues all TMA traffic ----------------
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = it_lo; it < it_hi; ++it) {
-        mbar_wait(bars + 8 * (STAGES + stage), phase ^ 1);
-        const uint32_t full = bars + 8 * stage;
-        mbar_arrive_expect_tx(full, STAGE_BYTES);
-        const uint32_t sa = tiles_u32 + stage * STAGE_BYTES;
-        const uint32_t sb = sa + TILE_BYTES;
-        const int k0 = it * BK;
-        if (A_KC) {
-          tma_load_2d(sa, &tmA, k0, m0, full);
-        } else {
-#pragma unroll
-          for (int b = 0; b < 8; ++b) tma_load_2d(sa + b * 2048, &tmA, m0 + 16 * b, k0, full);
-        }
-        if (B_KC) {
-          tma_load_2d(sb, &tmB, k0, n0, full);
-        } else {
-#pragma unroll
-          for (int b = 0; b < 8; ++b) tma_load_2d(sb + b * 2048, &tmB, n0 + 16 * b, k0, full);
-        }
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  // ---------------- producer role: thread 0 issues all TMA traffic ----------------
+  // There is no dedicated producer warp: a ninth warp would put three warps on one scheduler
+  // and cap every thread at 168 registers (64 accumulator doubles + fragments need ~180; the
+  // 9-warp build spilled into the main loop).  Thread 0 refills, at the top of iteration `it`, the
+  // stage of iteration it + LOOKAHEAD; that slot was consumed STAGES - LOOKAHEAD = 2 iterations
+  // ago, so the empty-barrier wait is satisfied unless a warp lags two iterations behind.
+  int pstage = 0;                 // producer ring position
+  uint32_t pphase = 0;
+  // Called by lane 0 of every warp.  A free-index-contiguous ("MC") operand tile is eight 16x16
+  // boxes: warp w issues box w, so no single warp carries all the copy instructions (one thread
+  // issuing 16 copies per iteration slowed its warp, and with it the ring, by ~10 %); a
+  // k-contiguous tile is one box, issued by warp 0.  Thread 0 posts the transaction count; a copy
+  // that completes before the count is posted just drives it negative for a moment, the phase
+  // cannot complete before thread 0's arrival.
+  auto issue = [&](int it) {
+    const bool work = (warp == 0) || !A_KC || !B_KC;
+    if (work) {
+      mbar_wait(bars + 8 * (STAGES + pstage), pphase ^ 1);
+      const uint32_t full = bars + 8 * pstage;
+      if (warp == 0) mbar_arrive_expect_tx(full, STAGE_BYTES);
+      const uint32_t sa = tiles_u32 + pstage * STAGE_BYTES;
+      const uint32_t sb = sa + TILE_BYTES;
+      const int k0 = it * BK;
+      if (A_KC) {
+        if (warp == 0) tma_load_2d(sa, &tmA, k0, m0, full);
+      } else {
+        tma_load_2d(sa + warp * 2048, &tmA, m0 + 16 * warp, k0, full);
       }
-    } else if (g.beta != 0.0 && g.nsplit == 1) {
-      // The other 31 lanes pull this tile of C into L2 while the main loop runs.  Without it the
-      // CTAs of a wave (which run in lockstep) all miss to DRAM in their epilogues at the same
-      // moment: ~19 MB in and ~19 MB out in one burst, 8.5 us per tile with the tensor pipe idle
-      // (tools/syrk_probe.py: K = 512 update at 28 TFLOP/s with beta = 1 vs 31 with beta = 0).
-      for (int idx = lane - 1; idx < BM * (BN / 16); idx += 31) {
-        const int r = m0 + idx / (BN / 16), c = n0 + (idx % (BN / 16)) * 16;
-        if (r < g.M && c < g.N) prefetch_l2(g.C + (long)r * g.ldc + c);
+      if (B_KC) {
+        if (warp == 0) tma_load_2d(sb, &tmB, k0, n0, full);
+      } else {
+        tma_load_2d(sb + warp * 2048, &tmB, n0 + 16 * warp, k0, full);
       }
     }
-    return;
+    if (++pstage == STAGES) { pstage = 0; pphase ^= 1; }
+  };
+  if (lane == 0) {
+    if (warp == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    for (int it = it_lo; it < it_hi && it < it_lo + LOOKAHEAD; ++it) issue(it);
+  }
+  if (g.beta != 0.0 && g.nsplit == 1) {
+    // Pull this tile of C into L2 while the main loop runs.  Without it the CTAs of a wave (which
+    // run in lockstep) all miss to DRAM in their epilogues at the same moment: ~19 MB in and
+    // ~19 MB out in one burst, 8.5 us per tile with the tensor pipe idle (tools/syrk_probe.py:
+    // K = 512 update at 28 TFLOP/s with beta = 1 vs 31 with beta = 0).
+    for (int idx = threadIdx.x; idx < BM * (BN / 16); idx += GEMM_THREADS) {
+      const int r = m0 + idx / (BN / 16), c = n0 + (idx % (BN / 16)) * 16;
+      if (r < g.M && c < g.N) prefetch_l2(g.C + (long)r * g.ldc + c);
+    }
   }
 
-  // ---------------- consumers: DMMA over the staged tiles ----------------
+  // ---------------- all 8 warps: DMMA over the staged tiles ----------------
   const int wm = (warp >> 2) * 64;   // warp tile origin inside the CTA tile
   const int wn = (warp & 3) * 32;
   const int r8 = lane >> 2;
@@ -202,6 +216,8 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA,
     int stage = 0;
     uint32_t phase = 0;
     for (int it = it_lo; it < it_hi; ++it) {
+      if (lane == 0 && it + LOOKAHEAD < it_hi) issue(it + LOOKAHEAD);
+      __syncwarp();
       mbar_wait(bars + 8 * stage, phase);
       const uint8_t* st = tiles + stage * STAGE_BYTES;
 #pragma unroll
@@ -459,7 +475,8 @@ int gemm_launch(Workspace* ws, const GemmDesc& g, cudaStream_t stream, int scrat
     ka.ws = ws->splitk[scratch];
   }
 
-  ka.mt = mt; ka.nt = nt; ka.gn = std::min(nt, 12);
+  static const int strip = [] { const char* e = getenv("MUNK_GEMM_STRIP"); return e ? std::max(1, atoi(e)) : 12; }();
+  ka.mt = mt; ka.nt = nt; ka.gn = std::min(nt, strip);
   dim3 grid((unsigned)(mt * nt), 1, nsplit);
   int st;
   if (g.a_layout == OP_KC && g.b_layout == OP_KC) st = launch_variant<true, true>(ta, tb, ka, grid, stream);

@@ -163,3 +163,32 @@ extern "C" int munk_separate_scores_means(int n1, int n2, const double* S, long 
   MUNK_CUDA_TRY(cudaGetLastError());
   return MUNK_OK;
 }
+
+namespace munk {
+namespace {
+// out[p] = X[r[p], 0:k] . Z[0:k, c[p]]   — one warp per pair (the score S[r,c] of the factored
+// form S = X Z, without forming S).
+__global__ void __launch_bounds__(256)
+pair_dots_kernel(int npairs, const int* __restrict__ r, const int* __restrict__ c, int k,
+                 const double* __restrict__ X, long ldx, const double* __restrict__ Z, long ldz,
+                 double* __restrict__ out) {
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= npairs) return;
+  const int lane = threadIdx.x & 31;
+  const double* __restrict__ x = X + (long)r[p] * ldx;
+  const double* __restrict__ z = Z + c[p];
+  double s = 0.0;
+  for (int l = lane; l < k; l += 32) s += x[l] * z[(long)l * ldz];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[p] = s;
+}
+}  // namespace
+}  // namespace munk
+
+extern "C" int munk_pair_dots(int npairs, const int* r, const int* c, int k, const double* X, long ldx,
+                              const double* Z, long ldz, double* out, void* stream) {
+  if (npairs <= 0) return MUNK_OK;
+  pair_dots_kernel<<<(npairs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(npairs, r, c, k, X, ldx, Z, ldz, out);
+  MUNK_CUDA_TRY(cudaGetLastError());
+  return MUNK_OK;
+}

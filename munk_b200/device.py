@@ -191,14 +191,53 @@ class Device:
         A = self.assemble(n, edges_u, edges_v, lam)
         return self.inverse_factor(A, n)
 
-    def spd_solve_gram(self, G, k, B, ncols):
-        """Z = G^-1 B for the small SPD k x k Gram matrix (overwritten).  Raises
-        NotPositiveDefinite if a pivot of the Cholesky factorisation is not positive."""
-        Wg = self.inverse_factor(G, k)
+    def spd_solve_gram(self, G, k, B, ncols, weights=None):
+        """Z = pinv(G) B for the small k x k landmark Gram matrix (overwritten).
+
+        Fast path: Cholesky (G is SPD with a modest condition number whenever the landmark rows
+        are distinct rows of a kernel factor).  If a pivot is not positive, or the pivots span
+        more than ~3.5 decades (cond(G) beyond ~1e7, where a Cholesky solve could no longer meet
+        the 1e-8 score tolerance), the rank-revealing Jacobi solve (munk_sym_pinv_solve) takes
+        over and truncates the null space like np.linalg.pinv does.  self.last_rank holds the
+        rank that was used."""
+        G0 = G.clone()
+        linv = self.potrf(G, k, check_info=False)
+        bad = self.potrf_info()
+        if not bad:
+            d = torch.diagonal(G[:k, :k])
+            ratio = float((d.min() / d.max()) ** 2)
+            bad = not (ratio > 1e-7)
+        if bad:
+            if weights is None:
+                return self.sym_pinv_solve(G0, k, B, ncols)
+            # A source landmark listed c times counts c-fold in pinv's least-squares objective:
+            # pinv(M) B = pinv(D M') (D mean(B)) with D = diag(sqrt(c)).  (With full row rank the
+            # residual is zero and D drops out, which is why the Cholesky path ignores it.)
+            d = torch.sqrt(torch.as_tensor(np.asarray(weights, dtype=np.float64), device=self.torch_device))
+            G0[:k, :k] *= d[:, None] * d[None, :]
+            Bw = B.clone()
+            Bw[:k] *= d[:, None]
+            Z = self.sym_pinv_solve(G0, k, Bw, ncols)
+            Z[:k] *= d[:, None]
+            return Z
+        self.last_rank = k
+        Wg = self.trtri(G, k, linv)
         Y = self.empty(k, ncols)
         self.gemm(KC, MC, k, ncols, k, 1.0, Wg, B, 0.0, Y, KHI_M)      # Y = Wg B
         Z = self.empty(k, ncols)
         self.gemm(MC, MC, k, ncols, k, 1.0, Wg, Y, 0.0, Z, KLO_M)      # Z = Wg^T Y
+        return Z
+
+    def sym_pinv_solve(self, G, k, B, ncols, rcond=1e-15):
+        """Z = pinv(G) B by the device Jacobi eigen-solver (G overwritten)."""
+        Z = self.empty(k, ncols)
+        work = torch.empty(lib.munk_sym_pinv_work_bytes(k, ncols) // 8 + 2, dtype=torch.float64,
+                           device=self.torch_device)
+        rank = ctypes.c_int(0)
+        check(lib.munk_sym_pinv_solve(self._ws, k, _ptr(G), G.stride(0), ncols, _ptr(B), B.stride(0),
+                                      _ptr(Z), Z.stride(0), _ptr(work), rcond, ctypes.byref(rank),
+                                      self.stream()), "munk_sym_pinv_solve")
+        self.last_rank = rank.value
         return Z
 
     def project(self, Q1, n1, B, n2, groups):
@@ -210,16 +249,30 @@ class Device:
         rows M M^T = D1[Ls,Ls] is a principal submatrix of an SPD matrix, so it is SPD with
         condition <= cond(D1) and the Gram/Cholesky route is the exact pinv.
         """
+        Z, kq = self.landmark_solve(Q1, n1, B, n2, groups)
+        P = self.empty(n1, n2)
+        self.gemm(KC, MC, n1, n2, kq, 1.0, Q1, Z, 0.0, P, 0)           # P = M^T Z
+        return P
+
+    def landmark_solve(self, Q1, n1, B, n2, groups):
+        """Z = (M M^T)^-1 mean_groups(B)  (k' x n2) and k', the factor shared by `project`
+        (P = M^T Z) and by the rank-k statistic (S = D1[:,Ls] Z)."""
         gptr, members = groups
         kq = len(gptr) - 1
         if any(gptr[g + 1] - gptr[g] != 1 for g in range(kq)) or list(members) != list(range(kq)):
             B = self.group_mean_rows(B, n2, gptr, members)
         G = self.empty(kq, kq)
         self.gemm(MC, MC, kq, kq, n1, 1.0, Q1, Q1, 0.0, G, 0)          # G = M M^T
-        Z = self.spd_solve_gram(G, kq, B, n2)
-        P = self.empty(n1, n2)
-        self.gemm(KC, MC, n1, n2, kq, 1.0, Q1, Z, 0.0, P, 0)           # P = M^T Z
-        return P
+        mult = [gptr[g + 1] - gptr[g] for g in range(kq)]
+        return self.spd_solve_gram(G, kq, B, n2, weights=mult if max(mult) > 1 else None), kq
+
+    def pair_dots(self, X, Z, k, rows, cols):
+        """out[p] = X[rows[p], :k] . Z[:k, cols[p]]"""
+        r, c = self.ints(rows), self.ints(cols)
+        out = torch.empty(int(r.numel()), dtype=torch.float64, device=self.torch_device)
+        check(lib.munk_pair_dots(int(r.numel()), _ptr(r), _ptr(c), k, _ptr(X), X.stride(0), _ptr(Z),
+                                 Z.stride(0), _ptr(out), self.stream()), "munk_pair_dots")
+        return out
 
     def trsm_left(self, L, n, linv, B, nrhs, transposed, stair=None):
         """B[:n, :nrhs] <- L^-1 B or L^-T B in place (factor + leaf inverses from potrf).

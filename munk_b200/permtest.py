@@ -96,6 +96,49 @@ class FactoredPair:
         return plan.means(dev, S)
 
 
+    def statistic_rank_k(self, homolog_idxs, n_landmarks):
+        """The same three numbers WITHOUT forming S (opt-in fast path).
+
+        With distinct source landmarks S = C1 C2hat^T = X Z with X = D1[:,Ls] = W1^T Q1 (n1 x k)
+        and Z = D1[Ls,Ls]^-1 mean_groups(D2[Lt,:]) (k x n2), so
+            sum over a row set R and a column set C of S  =  (1_R^T X) (Z 1_C)
+        and a single score is a k-long dot product.  Cost per permutation: n1^2 k flops for X
+        instead of n1^2 n2 for S (about 16x less time at 20k/16k/400).  Returns a host tuple
+        (hom_mean, other_mean, diff); validated against `statistic` in the GPU tests."""
+        from .device import KC, MC, KLO_M
+        dev, n1, n2 = self.dev, self.n1, self.n2
+        landmark_idxs = homolog_idxs[:n_landmarks]
+        uniq, gptr, members = landmark_groups([int(a) for a, _ in landmark_idxs])
+        Q1 = dev.gather_cols_lower(self.W1, n1, uniq)
+        B = dev.target_landmark_rows(self.W2, n2, [int(b) for _, b in landmark_idxs])
+        Z, kq = dev.landmark_solve(Q1, n1, B, n2, (gptr, members))
+        X = self._d1_columns(Q1, kq, dev.empty(n1, kq))
+        plan = plan_separate_scores(n1, n2, landmark_idxs, homolog_idxs)
+        # masks as n x 2 operands (second column zero): a = X^T m_R, b = Z m_C on the tensor cores
+        mR = torch.zeros((n1, 2), dtype=torch.float64, device=dev.torch_device)
+        mR[:, 0] = torch.from_numpy(1.0 - plan.rowL.astype(np.float64)).to(dev.torch_device)
+        mC = torch.zeros((n2, 2), dtype=torch.float64, device=dev.torch_device)
+        mC[:, 0] = torch.from_numpy(1.0 - plan.colL.astype(np.float64)).to(dev.torch_device)
+        a = dev.empty(kq, 2, ld=2)
+        dev.gemm(MC, MC, kq, 1, n1, 1.0, X, mR, 0.0, a, 0)            # a[l] = sum_{i not in R} X[i,l]
+        b = dev.empty(kq, 2, ld=2)
+        dev.gemm(KC, MC, kq, 1, n2, 1.0, Z, mC, 0.0, b, 0)            # b[l] = sum_{j not in C} Z[l,j]
+        hh = dev.pair_dots(X, Z, kq, plan.h_row, plan.h_col)
+        in_other = torch.from_numpy(((plan.rowL[plan.h_row] == 0) & (plan.colL[plan.h_col] == 0))
+                                    .astype(np.float64)).to(dev.torch_device)
+        block_sum = float((a[:, 0] * b[:, 0]).sum())
+        hh_sum, hh_other = float(hh.sum()), float((hh * in_other).sum())
+        hom_mean = hh_sum / plan.n_hh
+        other_mean = (block_sum - hh_other) / plan.n_other
+        return hom_mean, other_mean, hom_mean - other_mean
+
+    def _d1_columns(self, Q1, kq, X):
+        """X = D1[:, Ls] = W1^T Q1 (n1 x k'), contracting only k >= row of the triangular W1."""
+        from .device import MC, KLO_M
+        self.dev.gemm(MC, MC, self.n1, kq, self.n1, 1.0, self.W1, Q1, 0.0, X, KLO_M)
+        return X
+
+
 def permuted_homolog_idxs(homolog_idxs, p):
     """Permutation p of the 'indices' mode: seeded shuffle of the homolog index pairs."""
     order = np.random.default_rng(1000 + p).permutation(len(homolog_idxs))

@@ -219,6 +219,48 @@ def test_staircase_solve_matches_dense(dev):
     assert float(X[:, len(own):n_own_pad].abs().max()) == 0.0
 
 
+def test_rank_deficient_landmark_rows_follow_pinv(dev):
+    """Landmark rows that are linearly dependent without being duplicates: np.linalg.pinv
+    truncates the null direction; the Gram/Cholesky fast path cannot, so the Jacobi fallback
+    (munk_sym_pinv_solve) must take over and give the same minimum-norm answer."""
+    import munk_b200
+    rng = np.random.default_rng(11)
+    C = rng.standard_normal((60, 60))
+    C[41] = C[3] + 0.5 * C[17]                                   # dependent, not a duplicate
+    D2 = rng.standard_normal((50, 50))
+    idx = [(3, 1), (17, 4), (41, 7), (8, 9), (22, 30), (3, 12)]   # plus a true duplicate (3 twice)
+    _, want = oracle.embed_matrices(C, D2, idx)
+    _, got = munk_b200.embed_matrices(C, D2, idx)
+    assert dev.last_rank == 4                                     # 5 distinct rows, one dependent
+    assert oracle.rel_max_err(got, want) < 1e-9
+    # the device eigen-solver on its own: pinv of a PSD matrix of known rank
+    import torch
+    X = torch.randn(40, 25, dtype=torch.float64, device="cuda")
+    G = dev.empty(40, 40); G[:, :40] = X @ X.t()                  # rank 25
+    B = dev.empty(40, 30); B[:, :30] = torch.randn(40, 30, dtype=torch.float64, device="cuda")
+    ref = torch.linalg.pinv(G[:, :40].clone(), hermitian=True) @ B[:, :30]
+    Z = dev.sym_pinv_solve(G, 40, B, 30)
+    assert dev.last_rank == 25
+    assert relerr(Z[:, :30], ref) < 1e-9
+
+
+def test_rank_k_statistic_matches_dense_path(dev):
+    """Opt-in fast path (no S formed) vs the dense unit, incl. a repeated source landmark and
+    homolog cells inside landmark rows/columns."""
+    from munk_b200 import permtest, pipeline, synthetic
+    G1, G2, homs = synthetic.make_case(900, 700, 4, 120, seeds=(61, 62))
+    homs = homs[:5] + [(homs[2][0], homs[40][1]), (homs[50][0], homs[3][1])] + homs[5:]
+    k = 25
+    inp = pipeline.graph_inputs(G1, G2, homs, k)
+    hidx = [(inp["s_pos"][a], inp["t_pos"][b]) for a, b in homs]
+    pair = permtest.FactoredPair(dev, 900, inp["edges1"], 700, inp["edges2"])
+    for p in (None, 0, 1):
+        idx = hidx if p is None else permtest.permuted_homolog_idxs(hidx, p)
+        dense = pair.statistic(idx, k).cpu().numpy()[:3]
+        fast = pair.statistic_rank_k(idx, k)
+        assert np.allclose(fast, dense, rtol=1e-9, atol=0), (fast, dense)
+
+
 def test_random_network_generator(dev):
     """gen_random_network_data (gen_random_network.py:78-84): same nodes and degrees as the seed
     graph, D and C consistent with the oracle on the generated graph."""
