@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "MUNK pipeline FP64 TFLOP/s (useful flops / end-to-end s), 20k->16k nodes"
 UNIT = "TFLOP/s"
+# DRAM bytes (read + write) of the C3 score launch, ncu --set full, profiles/r01_ncu_summary.md
+NCU_SCORE_TRAFFIC_BYTES = 38.5e9
 
 
 def pipeline_flops(n1, n2, k):
@@ -372,7 +374,12 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-                         "frac": achieved / dmma_peak, "traffic": None,
+                         "frac": achieved / dmma_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch at C3 from the
+                         # ncu --set full capture in profiles/ (null for other configs: not captured)
+                         "traffic": NCU_SCORE_TRAFFIC_BYTES if args.config == "C3" else None,
+                         "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, one launch; algorithmic "
+                                           "bytes of the launch: %.2f GB)" % ((n1 * n1 / 2 + 2 * n1 * n2) * 8 / 1e9),
                          "kernel": "dgemm_dmma_tma_kernel<MC,MC> score launch: S = W1^T P, %d x %d x %d, "
                                    "k >= row only (%.2f TFLOP)" % (n1, n2, n1, fl["score"] / 1e12),
                          "peak_source": "measured in this run: FP64 DMMA issue-rate microbenchmark "
@@ -528,8 +535,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="C3")
     ap.add_argument("--impl", default="munk_b200", choices=["munk_b200", "reference"])
-    ap.add_argument("--cpu-n1", dest="cpu_n1", type=int, default=3000)
-    ap.add_argument("--cpu-n2", dest="cpu_n2", type=int, default=2400)
+    ap.add_argument("--cpu-n1", dest="cpu_n1", type=int, default=5000)
+    ap.add_argument("--cpu-n2", dest="cpu_n2", type=int, default=4000)
     ap.add_argument("--cpu-max-steps", dest="cpu_max_steps", type=int, default=5)
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     args = ap.parse_args()

@@ -2,10 +2,11 @@
 //
 // B200 has no tcgen05 kind for f64, so the FP64 tensor path is the warp-level DMMA
 // (mma.sync.m8n8k4.f64).  The kernel is built around it:
-//   * one CTA = 128x128 output tile, 8 consumer warps (2x4, each 64x32 = 8x4 DMMA tiles,
-//     64 accumulator doubles per lane) + 1 producer warp;
+//   * one CTA = 128x128 output tile, 8 warps (2x4, each 64x32 = 8x4 DMMA tiles, 64 accumulator
+//     doubles per lane); lane 0 of the warps doubles as the TMA producer (no ninth warp: it
+//     would cap the kernel at 168 registers and spill into the main loop);
 //   * operands are staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) into a 6-stage
-//     ring of 128x16 (A) + 128x16 (B) tiles guarded by full/empty mbarriers;
+//     ring of 128x16 (A) + 128x16 (B) tiles guarded by full/empty mbarriers, 4 stages in flight;
 //   * either operand may be stored k-contiguous ("KC", rows of 16 doubles = 128 B) or
 //     free-index-contiguous ("MC", eight 16x16 boxes); one k-permutation inside the
 //     16-deep stage (k(j,s) below) makes the 64-bit fragment loads bank-conflict-free
