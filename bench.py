@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 METRIC = "MUNK pipeline FP64 TFLOP/s (useful flops / end-to-end s), 20k->16k nodes"
 UNIT = "TFLOP/s"
 # DRAM bytes (read + write) of the C3 score launch, ncu --set full, profiles/r01_ncu_summary.md
-NCU_SCORE_TRAFFIC_BYTES = 38.5e9
+NCU_SCORE_TRAFFIC_BYTES = 38.0e9
 
 
 def pipeline_flops(n1, n2, k):

@@ -235,25 +235,32 @@ def graph_inputs(source_G, target_G, homologs, n_landmarks):
     assert n_landmarks <= len(homologs)
     source_nodes = util.sorted_nodes(source_G)
     target_nodes = util.sorted_nodes(target_G)
+    return index_inputs(source_nodes, util.edge_index_arrays(source_G, source_nodes),
+                        target_nodes, util.edge_index_arrays(target_G, target_nodes), homologs, n_landmarks)
+
+
+def index_inputs(source_nodes, edges1, target_nodes, edges2, homologs, n_landmarks):
+    """The same from sorted node lists + edge index arrays (e.g. munk_b200.ingest.load_two_core),
+    without networkx graphs."""
+    assert n_landmarks <= len(homologs)
     s_pos = {name: i for i, name in enumerate(source_nodes)}
     t_pos = {name: i for i, name in enumerate(target_nodes)}
     landmark_homs = homologs[:n_landmarks]
     landmark_idxs = [(s_pos[a], t_pos[b]) for a, b in landmark_homs]
-    edges1 = util.edge_index_arrays(source_G, source_nodes)
-    edges2 = util.edge_index_arrays(target_G, target_nodes)
     return dict(source_nodes=source_nodes, target_nodes=target_nodes, s_pos=s_pos, t_pos=t_pos,
                 landmark_homs=landmark_homs, landmark_idxs=landmark_idxs, edges1=edges1, edges2=edges2)
 
 
 def embed_and_score(source_G, target_G, homologs, n_landmarks, src_lam=0.05, tgt_lam=0.05, dev=None,
-                    sink=None):
-    """Everything the CLI needs in one device-resident pass, results streamed to pinned host
-    memory while the remaining stages run (pass a reusable HostSink to avoid re-pinning).
+                    sink=None, inputs=None):
+    """Everything the CLI needs in one device-resident pass, results streamed to host memory
+    while the remaining stages run (pass a reusable pinned HostSink to avoid re-pinning).
+    `inputs` = index_inputs(...) replaces the two graphs (fast ingestion path, no networkx).
 
     Returns dict(source_X, target_X, scores, source_nodes, target_nodes, landmarks, runtimes).
     """
     dev = dev or default_device()
-    inp = graph_inputs(source_G, target_G, homologs, n_landmarks)
+    inp = inputs if inputs is not None else graph_inputs(source_G, target_G, homologs, n_landmarks)
     n1, n2 = len(inp["source_nodes"]), len(inp["target_nodes"])
     sink = sink or HostSink(dev, n1, n2, pinned=False)
     emb = embed_device(n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"], src_lam, tgt_lam,

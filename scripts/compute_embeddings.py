@@ -2,9 +2,12 @@
 """MUNK embeddings + similarity scores from two edge lists and a homolog list, on a B200.
 
 Drop-in for the reference CLI (scripts/compute_embeddings.py:17-31 flag surface, :72-98 output
-files and schemas).  The numeric work (both regularized-Laplacian kernels, the source RKHS
-factor, the landmark projection and the n1 x n2 score product) runs in one device-resident
-pass (munk_b200.pipeline.embed_and_score); only the three result matrices come back to the host.
+files and schemas).  Graph ingestion (parse, largest component, self loops, 2-core, sorted index
+map) runs on arrays (munk_b200.ingest, bit-exact with the reference's networkx path; pass
+--networkx_ingest to use networkx itself); the numeric work (both regularized-Laplacian kernels,
+the source RKHS factor, the landmark projection and the n1 x n2 score product) runs in one
+device-resident pass (munk_b200.pipeline.embed_and_score); the three result matrices stream back
+to the host while later stages are still computing.
 """
 import argparse
 import json
@@ -14,12 +17,11 @@ import sys
 import time
 
 import joblib
-import networkx as nx
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 
 import munk_b200 as munk  # noqa: E402
-from munk_b200 import pipeline, util  # noqa: E402
+from munk_b200 import ingest, pipeline, util  # noqa: E402
 
 REQUIRED = [
     ('-se', '--source_edgelist'), ('-te', '--target_edgelist'), ('-hf', '--homolog_list'),
@@ -37,12 +39,24 @@ def build_parser():
     ap.add_argument('-rs', '--random_seed', type=int, default=28791)
     ap.add_argument('--src_lam', type=float, default=0.05)
     ap.add_argument('--tgt_lam', type=float, default=0.05)
+    ap.add_argument('--networkx_ingest', action='store_true',
+                    help='load and prune the graphs with networkx (the reference path) instead of arrays')
     return ap
 
 
-def load_two_core(path, log, what):
+def load_with_networkx(path, log, what):
+    import networkx as nx
     log.info('Loading %s edgelist from %s', what, path)
-    return util.simple_two_core(nx.read_edgelist(path, encoding='ascii'))
+    G = util.simple_two_core(nx.read_edgelist(path, encoding='ascii'))
+    nodes = util.sorted_nodes(G)
+    return nodes, util.edge_index_arrays(G, nodes)
+
+
+def load_with_arrays(path, log, what):
+    log.info('Loading %s edgelist from %s', what, path)
+    nodes, u, v = ingest.load_two_core(path)
+    log.info('2 core info - # Nodes: %d, # Edges: %d', len(nodes), len(u))
+    return nodes, (u, v)
 
 
 def run(args):
@@ -51,14 +65,17 @@ def run(args):
 
     log.info('Loading homologs list from %s', args.homolog_list)
     raw_homologs = util.read_homolog_list(args.homolog_list)
-    source_G = load_two_core(args.source_edgelist, log, 'source')
-    target_G = load_two_core(args.target_edgelist, log, 'target')
-    homologs = util.homologs_in_graphs(source_G, target_G, raw_homologs)
+    load = load_with_networkx if args.networkx_ingest else load_with_arrays
+    source_nodes, source_edges = load(args.source_edgelist, log, 'source')
+    target_nodes, target_edges = load(args.target_edgelist, log, 'target')
+    homologs = ingest.homologs_in_node_lists(source_nodes, target_nodes, raw_homologs)
 
     log.info('Computing MUNK embeddings with %d landmarks', args.n_landmarks)
+    inputs = pipeline.index_inputs(source_nodes, source_edges, target_nodes, target_edges, homologs,
+                                   args.n_landmarks)
     started = time.time()
-    res = pipeline.embed_and_score(source_G, target_G, homologs, args.n_landmarks,
-                                   src_lam=args.src_lam, tgt_lam=args.tgt_lam)
+    res = pipeline.embed_and_score(None, None, homologs, args.n_landmarks, src_lam=args.src_lam,
+                                   tgt_lam=args.tgt_lam, inputs=inputs)
     total_time = time.time() - started
     landmarks = res['landmarks']
 
@@ -81,8 +98,7 @@ def run(args):
 
     log.info('Saving runtimes to %s', args.runtimes_file)
     with open(args.runtimes_file, 'w') as out:
-        json.dump(dict(n_source_nodes=source_G.number_of_nodes(),
-                       n_target_nodes=target_G.number_of_nodes(),
+        json.dump(dict(n_source_nodes=len(source_nodes), n_target_nodes=len(target_nodes),
                        runtimes=res['runtimes'], total_time=total_time), out, indent=2)
     log.info('MUNK embedding complete!')
 
