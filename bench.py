@@ -4,9 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config C3] [--impl reference]
 
 One "step" = the whole dense pipeline for one synthetic scale-free graph pair of the named
-configuration: Laplacian assembly, Cholesky + triangular inverse of
-source and target (C1 = W1^T, D2 = W2^T W2), landmark projection C2hat, and the n1 x n2 score
-product S = C1 C2hat^T.  At N=1 the workload is BASELINE.json's 20k -> 16k configuration (C3).
+configuration: Laplacian assembly of both graphs, Cholesky + triangular
+inverse of the source (C1 = L1^-T), Cholesky + k-column solves of the target (D2[Lt,:]), landmark
+projection C2hat, and the n1 x n2 score product S = C1 C2hat^T.  At N=1 the workload is
+BASELINE.json's 20k -> 16k configuration (C3); N>1 shards that one pipeline over the GPUs.
 
   value  = useful FP64 flops of the step (formulae of SURVEY 8d, triangular products counted once)
            x graph pairs processed by all ranks / device time (CUDA events, max over ranks), inputs
