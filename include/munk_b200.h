@@ -72,6 +72,10 @@ int munk_potrf(munk_workspace_t* ws, int n, double* A, long ld, double* linv, vo
  * the first bad column; the device flag is cleared. */
 int munk_potrf_info(munk_workspace_t* ws, int* info_host, void* stream);
 
+/* Same without synchronising: the flag is moved into the device int *info_dev (and cleared), so a
+ * caller can keep enqueuing work and inspect all its flags once at the end of a step. */
+int munk_potrf_info_async(munk_workspace_t* ws, int* info_dev, void* stream);
+
 /*
  * In-place W = L^-1 of the factor left by munk_potrf (same linv).  C = W^T is an RKHS factor of
  * D = A^-1 (C C^T = D); replaces scipy.linalg.eigh + v.dot(diag(sqrt(e))) at

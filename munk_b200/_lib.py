@@ -25,6 +25,7 @@ SIGNATURES = {
                                      c_void_p, c_long, c_void_p]),
     "munk_potrf": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p]),
     "munk_potrf_info": (c_int, [c_void_p, _P(c_int), c_void_p]),
+    "munk_potrf_info_async": (c_int, [c_void_p, c_void_p, c_void_p]),
     "munk_trtri": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p]),
     "munk_gram_lower": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p]),
     "munk_trsm_left": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_int, c_int, c_void_p,

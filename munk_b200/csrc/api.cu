@@ -103,6 +103,13 @@ int munk_potrf_info(munk_workspace_t* ws, int* info_host, void* stream) {
   return MUNK_OK;
 }
 
+int munk_potrf_info_async(munk_workspace_t* ws, int* info_dev, void* stream) {
+  if (!ws || !info_dev) return -1;
+  MUNK_CUDA_TRY(cudaMemcpyAsync(info_dev, ws->info, sizeof(int), cudaMemcpyDeviceToDevice, S(stream)));
+  MUNK_CUDA_TRY(cudaMemsetAsync(ws->info, 0, sizeof(int), S(stream)));
+  return MUNK_OK;
+}
+
 int munk_trtri(munk_workspace_t* ws, int n, double* L, long ld, double* linv, void* stream) {
   if (!ws) return -1;
   if (n < 0) return -2;

@@ -43,6 +43,23 @@ __global__ void __launch_bounds__(256) separate_scores_kernel(const SepArgs a) {
   double* __restrict__ o_lloff = a.out_lloff + a.off_lloff[i];
   double* __restrict__ o_lnonl = a.out_lnonl + a.off_lnonl[i];
   double* __restrict__ o_other = a.out_other + a.off_other[i];
+  // Fast path — a non-landmark row without homolog cells (all but ~k + H of the n1 rows): every
+  // element goes to "other" (non-landmark column) or "landmark x non-landmark" (landmark
+  // column); two elements per thread with 16-byte loads.
+  if (!rl && hlo == hhi && (a.lds & 1) == 0 && (a.n2 & 1) == 0 && ((uintptr_t)a.S & 15) == 0) {
+    const double2* __restrict__ row2 = reinterpret_cast<const double2*>(row);
+    const uchar2* __restrict__ cl2 = reinterpret_cast<const uchar2*>(a.colL);
+    const int2* __restrict__ rk2 = reinterpret_cast<const int2*>(a.colrank);
+    for (int p = blockIdx.y * blockDim.x + threadIdx.x; p < (a.n2 >> 1); p += gridDim.y * blockDim.x) {
+      const double2 v = row2[p];
+      const uchar2 cl = cl2[p];
+      const int2 rk = rk2[p];
+      const int j = 2 * p;
+      if (cl.x) o_lnonl[rk.x] = v.x; else o_other[j - rk.x] = v.x;
+      if (cl.y) o_lnonl[rk.y] = v.y; else o_other[j + 1 - rk.y] = v.y;
+    }
+    return;
+  }
   for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < a.n2; j += gridDim.y * blockDim.x) {
     const double v = row[j];
     const bool cl = a.colL[j] != 0;

@@ -128,6 +128,12 @@ class Device:
         check(lib.munk_potrf_info(self._ws, ctypes.byref(info), self.stream()), "munk_potrf_info")
         return info.value
 
+    def potrf_info_async(self):
+        """The status flag moved into a fresh 1-element int32 CUDA tensor (flag cleared); no sync."""
+        out = torch.empty(1, dtype=torch.int32, device=self.torch_device)
+        check(lib.munk_potrf_info_async(self._ws, _ptr(out), self.stream()), "munk_potrf_info_async")
+        return out
+
     def raise_if_not_spd(self):
         info = self.potrf_info()
         if info:

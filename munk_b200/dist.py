@@ -301,11 +301,9 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
     main.wait_stream(side)
     for t in (A2, linv2, B):
         t.record_stream(main)
-    bad = max(dist_potrf_flag(ops, dev.torch_device, world, group),
-              dist_potrf_flag(ops2, dev.torch_device, world, group))
-    if bad:
-        from .device import NotPositiveDefinite
-        raise NotPositiveDefinite("matrix is not positive definite (pivot %d)" % (bad - 1))
+    # the factorisation flags are parked in device ints (no host sync here: the host keeps
+    # enqueuing) and inspected once at the end of the step
+    flags = torch.cat([dev.potrf_info_async(), dev2.potrf_info_async()]).to(torch.int64)
     P = dev.project(Q1, n1, B, n2, (gptr, members))
 
     mark("embed")
@@ -317,6 +315,13 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
     C1 = X[:, :m_own].t() if m_own else X[:, :0].t()            # (m_own, n1) view of the solve
 
     mark("score")
+    bad = flags.max().reshape(1)
+    if world > 1:
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
+    bad = int(bad.item())
+    if bad:
+        from .device import NotPositiveDefinite
+        raise NotPositiveDefinite("matrix is not positive definite (pivot %d)" % (bad - 1))
     out = dict(rows=rows, C1=C1, P=P, S=S[:m_own], n1=n1, n2=n2)
     if homolog_idxs is not None:
         out["stats"] = dist_score_means(dev, S, rows, n1, n2, landmark_idxs, homolog_idxs, world, group)

@@ -75,7 +75,13 @@ class SeparatePlan:
 
     # ---- device side ----------------------------------------------------------------------
     def _dev(self, dev, arr):
-        return torch.from_numpy(np.ascontiguousarray(arr)).to(dev.torch_device)
+        """Device copy of a plan array, uploaded once per (plan, device)."""
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        key = (dev.index, id(arr))
+        t = cache.get(key)
+        if t is None:
+            t = cache[key] = (arr, torch.from_numpy(np.ascontiguousarray(arr)).to(dev.torch_device))
+        return t[1]
 
     def run(self, dev, S, to_host=True):
         """Five arrays as separate_scores returns them (numpy if to_host else CUDA tensors)."""
