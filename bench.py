@@ -299,7 +299,7 @@ def run_gpu(args):
     # C1, C2hat^T and S streamed to the pinned buffers of a HostSink while later stages compute.
     sink = pipeline.HostSink(dev, n1, n2)
     h2d = sum(t.numel() * t.element_size() for t in h_e1 + h_e2) + 8 * len(t_idx)
-    d2h = sum(t.numel() * t.element_size() for t in (sink.C1, sink.P, sink.S))
+    d2h = sink.d2h_bytes()
 
     def e2e_step():
         emb = pipeline.embed_device(n1, h_e1, n2, h_e2, inp["landmark_idxs"], dev=dev,

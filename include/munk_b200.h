@@ -133,6 +133,18 @@ int munk_gather_cols_lower(int n, const double* W, long ldw, int k, const int* i
 /* C[i][j] = W[j][i] for j >= i, else 0: materialises the upper-triangular factor C = W^T. */
 int munk_transpose_lower(int n, const double* W, long ldw, double* C, long ldc, void* stream);
 
+/*
+ * Device -> host copy of the upper-triangular factor C (n x n on the device, row-major) into the
+ * host array `host` (row-major, ldh elements per row): row block b of `row_block` rows copies the
+ * columns from its first row index onwards, i.e. every non-zero of C and at most row_block - 1
+ * structural zeros per row; the strictly lower part of `host` is NOT written (the caller zeroes it
+ * once).  Halves the bytes moved for the array the reference pickles as the source embedding
+ * (scripts/compute_embeddings.py:72, munk/munk/munk.py:178-180).  Asynchronous on `stream`
+ * when `host` is page-locked.
+ */
+int munk_download_upper(int n, const double* C, long ldc, double* host, long ldh, int row_block,
+                        void* stream);
+
 /* out[g][:] = mean of in[members[gptr[g] .. gptr[g+1])][:]; used to fold duplicated source
  * landmarks (np.linalg.pinv's minimum-norm least-squares answer, munk/munk/munk.py:109). */
 int munk_group_mean_rows(int ngroups, const int* gptr, const int* members, int ncols,

@@ -195,6 +195,24 @@ int munk_transpose_lower(int n, const double* W, long ldw, double* C, long ldc, 
   return transpose_lower(n, W, ldw, C, ldc, S(stream));
 }
 
+int munk_download_upper(int n, const double* C, long ldc, double* host, long ldh, int row_block,
+                        void* stream) {
+  if (n < 0) return -1;
+  if (!C && n > 0) return -2;
+  if (ldc < n) return -3;
+  if (!host && n > 0) return -4;
+  if (ldh < n) return -5;
+  if (row_block <= 0) return -6;
+  for (long r0 = 0; r0 < n; r0 += row_block) {
+    long rows = (n - r0 < row_block) ? (n - r0) : row_block;
+    MUNK_CUDA_TRY(cudaMemcpy2DAsync(host + r0 * ldh + r0, (size_t)ldh * sizeof(double),
+                                    C + r0 * ldc + r0, (size_t)ldc * sizeof(double),
+                                    (size_t)(n - r0) * sizeof(double), (size_t)rows,
+                                    cudaMemcpyDeviceToHost, S(stream)));
+  }
+  return MUNK_OK;
+}
+
 int munk_copy_lower(int n, const double* in, long ldi, double* out, long ldo, void* stream) {
   return copy_lower(n, in, ldi, out, ldo, S(stream));
 }

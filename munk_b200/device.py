@@ -176,6 +176,15 @@ class Device:
               "munk_copy_lower")
         return out
 
+    def download_upper(self, C, n, host, row_block=1024):
+        """host[i, j] <- C[i, j] for the upper-triangular C (device), in row blocks that skip the
+        zero part left of each block's first column; `host` (a CPU tensor whose strictly lower
+        part is already zero) receives half the bytes of a full copy.  Enqueued on the current
+        stream; asynchronous if `host` is pinned."""
+        assert host.device.type == "cpu" and host.dtype == torch.float64 and host.stride(1) == 1
+        check(lib.munk_download_upper(n, _ptr(C), C.stride(0), host.data_ptr(), host.stride(0),
+                                      row_block, self.stream()), "munk_download_upper")
+
     def group_mean_rows(self, B, ncols, gptr, members):
         g = len(gptr) - 1
         out = self.empty(g, ncols)

@@ -16,6 +16,8 @@ import torch
 from . import util
 from .device import MC, NotPositiveDefinite, default_device, landmark_groups, side_device
 
+B200_SMS = 148
+
 
 class PhaseTimer:
     """Wall-clock phase timers bracketed by a stream synchronise (reference keys,
@@ -58,6 +60,8 @@ class HostSink:
         self.pinned = pinned
         opts = dict(dtype=torch.float64, pin_memory=pinned)
         self.C1 = torch.empty((n1, n1), **opts)
+        if pinned or prefault_threads <= 0:
+            self.C1.zero_()                # the lower triangle stays zero; copies skip it
         self.P = torch.empty((n1, n2), **opts)
         self.S = torch.empty((n1, n2), **opts)
         self.dev = dev
@@ -91,14 +95,17 @@ class HostSink:
         src.record_stream(self.stream)
 
     def push_source_factor(self, W1, n1):
-        """C1 = W1^T: transpose on the copy stream, then out."""
+        """C1 = W1^T: transpose on the copy stream, then out.  C1 is upper triangular, so only
+        the part right of each row block's first column travels (half the bytes); the strictly
+        lower part of the host buffer was zeroed when the sink was created and is never written."""
         self.stream.wait_stream(torch.cuda.current_stream(self.dev.index))
         with torch.cuda.stream(self.stream):
             C = self.dev.transpose_lower(W1, n1, ld=n1 + (n1 & 1))
             if self.pinned:
-                self.C1.copy_(C[:, :n1], non_blocking=True)
+                self.dev.download_upper(C, n1, self.C1)
+                C.record_stream(self.stream)
             else:
-                self._pending.append((self.C1, C[:, :n1]))
+                self._pending.append((self.C1, C, n1))
         W1.record_stream(self.stream)
 
     def wait(self):
@@ -107,9 +114,20 @@ class HostSink:
         self._threads = []
         torch.cuda.current_stream(self.dev.index).synchronize()
         self.stream.synchronize()
-        for dst, src in self._pending:
-            dst.copy_(src)
+        for item in self._pending:
+            if len(item) == 3:                       # (host C1, device C, n1): triangular copy
+                self.dev.download_upper(item[1], item[2], item[0])
+            else:
+                item[0].copy_(item[1])
+        if self._pending:
+            torch.cuda.current_stream(self.dev.index).synchronize()
         self._pending = []
+
+    def d2h_bytes(self, row_block=1024):
+        """Bytes one pipeline run copies device -> host through this sink (C1 triangular)."""
+        n1 = self.C1.shape[0]
+        c1 = sum((n1 - r0) * min(row_block, n1 - r0) for r0 in range(0, n1, row_block)) * 8
+        return c1 + (self.P.numel() + self.S.numel()) * 8
 
     def arrays(self):
         """(C1, C2hat, S) as numpy arrays over the pinned buffers; C2hat is the transposed view the
@@ -131,21 +149,27 @@ class DeviceEmbedding:
             self._S = self.dev.score(self.W1, self.n1, self.P, self.n2)
         return self._S
 
-    def scores_streamed(self, sink, row_blocks=4):
-        """S = W1^T P in `row_blocks` row blocks (each one DMMA launch; the k-range of a block
-        starts at its first row, so the triangular saving is kept); every finished block is
-        copied to sink.S on the copy stream while the next one is computed."""
+    def scores_streamed(self, sink, cuts=(0.04, 0.12, 0.3, 0.6)):
+        """S = W1^T P in row blocks (each one DMMA launch; the k-range of a block starts at its
+        first row, so the triangular saving is kept), bottom block first; every finished block is
+        copied to sink.S on the copy stream while the next one is computed.  Rows near the top
+        contract over the longest k-range, so the order is bottom-up and the last block is a thin
+        one (`cuts` = block boundaries as fractions of the rows): its long compute hides the
+        copy of the block before it and only its own small copy is left after the last launch."""
         dev, n1, n2 = self.dev, self.n1, self.n2
         S = dev.empty(n1, n2)
         tiles = (n1 + 127) // 128
-        per = (tiles + row_blocks - 1) // row_blocks
-        for b in range(row_blocks):
-            r0, r1 = min(n1, b * per * 128), min(n1, (b + 1) * per * 128)
-            if r1 <= r0:
-                continue
-            stair = dev.ints([r0 + 128 * t for t in range((r1 - r0 + 127) // 128)])
+        edges = {0, tiles} | {min(tiles, max(0, int(round(c * tiles)))) for c in cuts[1:]}
+        # the thin last block has equal-length tiles: pick its height so they fill whole waves
+        col_tiles, want = (n2 + 127) // 128, max(1, int(round(cuts[0] * tiles)))
+        thin = min(range(max(1, want - 2), want + 3),
+                   key=lambda t: (-(t * col_tiles) % B200_SMS) / float(t * col_tiles))
+        edges = sorted(edges | {min(tiles, thin)})
+        stair_all = dev.ints([128 * t for t in range(tiles)])
+        for t0, t1 in reversed(list(zip(edges[:-1], edges[1:]))):
+            r0, r1 = t0 * 128, min(n1, t1 * 128)
             dev.gemm_stair(MC, MC, r1 - r0, n2, n1, 1.0, self.W1[:, r0:], self.P, 0.0, S[r0:], 0,
-                           stair_m=stair, k0=0)
+                           stair_m=stair_all[t0:t1], k0=0)
             sink.push(sink.S[r0:r1], S[r0:r1, :n2])
         self._S = S
         return S
@@ -218,13 +242,15 @@ def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.
             A2 = dev.assemble(n2, edges2[0], edges2[1], tgt_lam)
             linv2 = dev.potrf(A2, n2)
             B = dev.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
-    if sink is not None:
-        sink.push_source_factor(W1, n1)          # C1 leaves while the projection and scores run
     with timer("embed_runtime"):
         Q1 = dev.gather_cols_lower(W1, n1, uniq)
         P = dev.project(Q1, n1, B, n2, (gptr, members))
         dev.raise_if_not_spd()
     if sink is not None:
+        # C1 and P leave while the scores are computed.  Pushed only now: the projection reads
+        # small status values back to the host, and such a read queues behind any bulk
+        # device-to-host copy already in flight (measured: the host stalled for the whole C1 copy).
+        sink.push_source_factor(W1, n1)
         sink.push(sink.P, P[:, :n2])
     return DeviceEmbedding(dev, n1, n2, W1, A2 if keep_target_factor else None, P, timer.times)
 

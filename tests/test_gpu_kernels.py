@@ -180,6 +180,27 @@ def test_streamed_outputs_equal_direct_outputs(dev):
     assert oracle.rel_max_err(res["scores"], oracle.scores(ref["C1"], ref["C2"])) < 1e-11
 
 
+@pytest.mark.parametrize("n,row_block,pinned", [(1, 4, False), (37, 8, True), (300, 128, True),
+                                                (1029, 1024, False)])
+def test_download_upper_moves_exactly_the_triangle(dev, n, row_block, pinned):
+    """munk_download_upper: bit-exact upper triangle on the host, strictly lower part untouched."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(n)
+    full = torch.randn(n, n + 3, dtype=torch.float64, generator=g)
+    C = torch.triu(full[:, :n]).contiguous()
+    Cd = torch.zeros(n, n + 3, dtype=torch.float64, device=dev.torch_device)
+    Cd[:, :n] = C.to(dev.torch_device)
+    host = torch.full((n, n + 1), -7.0, dtype=torch.float64, pin_memory=pinned)
+    dev.download_upper(Cd, n, host, row_block=row_block)
+    torch.cuda.synchronize()
+    got = host[:, :n]
+    assert torch.equal(torch.triu(got), C)
+    blk = torch.arange(n) // row_block * row_block               # first column each row receives
+    untouched = torch.arange(n)[None, :] < blk[:, None]
+    assert bool((got[untouched] == -7.0).all()) and bool((host[:, n] == -7.0).all())
+    assert bool((got[~untouched & (torch.arange(n)[None, :] < torch.arange(n)[:, None])] == 0).all())
+
+
 def test_distributed_driver_single_rank_matches_oracle(dev):
     """munk_b200.dist with world = 1 (same code path as N ranks, minus the broadcasts): panel
     driver, staircase solve for the W columns + landmark columns, staircase score product, means."""
