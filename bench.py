@@ -54,7 +54,9 @@ def pipeline_flops(n1, n2, k):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md clocks line), read
+    in-process through NVML every 50 ms (a spawned nvidia-smi per sample costs ~100 ms of driver
+    time each and perturbs host-driven steps); nvidia-smi is the fallback if NVML is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -62,18 +64,43 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu_index, self.rows, self._halt = gpu_index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if visible and all(x.strip().isdigit() for x in visible.split(",")):
+                phys = int(visible.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self.nvml, self.handle
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        act = lambda bit: "Active" if mask & bit else "Not Active"  # noqa: E731
+        return [str(sm), str(mx), "", act(nv.nvmlClocksEventReasonHwSlowdown),
+                act(nv.nvmlClocksEventReasonHwThermalSlowdown), act(nv.nvmlClocksEventReasonSwThermalSlowdown),
+                act(nv.nvmlClocksEventReasonSwPowerCap)]
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(float(os.environ.get("MUNK_BENCH_CLOCK_PERIOD", "0.05" if self.nvml is not None else "0.2")))
 
     def stop(self):
         self._halt.set()
@@ -89,7 +116,8 @@ class ClockSampler(threading.Thread):
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "via": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_inputs(cfg_name, rank, n1=None, n2=None):
@@ -100,6 +128,15 @@ def make_inputs(cfg_name, rank, n1=None, n2=None):
     G1, G2, homs = synthetic.make_case(n1, n2, m, min(H, n1, n2), seeds=(1 + 2 * rank, 2 + 2 * rank))
     inp = pipeline.graph_inputs(G1, G2, homs, min(k, len(homs)))
     return n1, n2, len(inp["landmark_idxs"]), inp, (G1, G2, homs)
+
+
+def _settle_gc():
+    """The synthetic networkx graphs (millions of Python objects) are scaffolding: drop them and
+    park what is left in the permanent generation, so that a full garbage collection does not
+    stall the host-driven panel loops for tens of ms in the middle of a timed step."""
+    import gc
+    gc.collect()
+    gc.freeze()
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -204,6 +241,8 @@ def run_gpu(args):
     if world > 1 and args.mode == "strong":
         return run_gpu_dist(args, dev, rank, world, local)
     n1, n2, k, inp, graphs = make_inputs(args.config, rank)
+    graphs = None
+    _settle_gc()
     fl = pipeline_flops(n1, n2, k)
     tdev = dev.torch_device
 
@@ -415,6 +454,8 @@ def run_gpu_dist(args, dev, rank, world, local):
     from munk_b200._lib import lib
 
     n1, n2, k, inp, _ = make_inputs(args.config, 0)            # same graph pair on every rank
+    _ = None
+    _settle_gc()
     fl = pipeline_flops(n1, n2, k)
     tdev = dev.torch_device
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -422,15 +463,18 @@ def run_gpu_dist(args, dev, rank, world, local):
     e2 = (dev.ints(inp["edges2"][0]), dev.ints(inp["edges2"][1]))
     phase_ms = {}
 
-    def step(edges1, edges2, record=False):
+    def step(edges1, edges2, record=False, sink=None):
         marks = [] if record else None
         out = mdist.dist_embed_scores(dev, n1, edges1, n2, edges2, inp["landmark_idxs"], rank, world,
-                                      marks=marks)
+                                      marks=marks, sink=sink)
         if record:
             torch.cuda.current_stream().synchronize()
             for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
                 phase_ms.setdefault(name, []).append(a.elapsed_time(b))
+            step_ends.append((marks[0][1], marks[-1][1], time.perf_counter()))
         return out
+
+    step_ends = []
 
     def barrier():
         dist.barrier()
@@ -445,31 +489,41 @@ def run_gpu_dist(args, dev, rank, world, local):
     t0, t1 = ev(), ev()
     t0.record()
     for _ in range(args.steps):
-        out = step(e1, e2, record=True)
+        step(e1, e2, record=True)          # result dropped at once: keeping it alive would make the
+        #                                    next step allocate a second set of n1 x n2 buffers
     t1.record()
     barrier()
     ms = t0.elapsed_time(t1)
     launches, counted_flops = dev.stats(reset=True)
     clocks = sampler.stop()
+    print("rank %d: %.1f ms/step, phases %s" % (rank, ms / args.steps, {
+        kk: round(statistics.median(vv), 1) for kk, vv in phase_ms.items()}), file=sys.stderr, flush=True)
+    if os.environ.get("MUNK_BENCH_TRACE"):
+        gaps = [round(t0.elapsed_time(step_ends[0][0]), 1)] + [
+            round(a[1].elapsed_time(b[0]), 1) for a, b in zip(step_ends[:-1], step_ends[1:])] + [
+            round(step_ends[-1][1].elapsed_time(t1), 1)]
+        walls = [round((b[2] - a[2]) * 1e3, 1) for a, b in zip(step_ends[:-1], step_ends[1:])]
+        print("rank %d: device-idle gaps before/between/after steps (ms) %s, host wall per step %s, phases per step %s" % (
+            rank, gaps, walls, {kk: [round(x, 1) for x in vv] for kk, vv in phase_ms.items()}),
+            file=sys.stderr, flush=True)
 
-    # e2e: host edge arrays in, every rank's shard of C1 and S (and P on rank 0) out to pinned memory
-    m_own = len(out["rows"])
+    # e2e: host edge arrays in; every rank's rows of C1, S and C2hat out to pinned memory through a
+    # ShardSink (copies on a second stream, overlapping the remaining stages)
     h_e1 = [torch.from_numpy(x).pin_memory() for x in inp["edges1"]]
     h_e2 = [torch.from_numpy(x).pin_memory() for x in inp["edges2"]]
-    out_C1 = torch.empty((m_own, n1), dtype=torch.float64, pin_memory=True)
-    out_S = torch.empty((m_own, n2), dtype=torch.float64, pin_memory=True)
-    out_P = torch.empty((n1, n2), dtype=torch.float64, pin_memory=True) if rank == 0 else None
+    sink = mdist.ShardSink(dev, n1, n2, rank, world)
     h2d = sum(t.numel() * t.element_size() for t in h_e1 + h_e2)
-    d2h = out_C1.numel() * 8 + out_S.numel() * 8 + (out_P.numel() * 8 if out_P is not None else 0)
+    d2h = sink.d2h_bytes()
+
+    trace = {}
 
     def e2e_step():
+        trace["start"] = ev(); trace["start"].record()
         d1 = [t.to(tdev, non_blocking=True) for t in h_e1]
         d2 = [t.to(tdev, non_blocking=True) for t in h_e2]
-        o = step(d1, d2)
-        out_C1.copy_(o["C1"], non_blocking=True)
-        out_S.copy_(o["S"][:, :n2], non_blocking=True)
-        if out_P is not None:
-            out_P.copy_(o["P"][:, :n2], non_blocking=True)
+        step(d1, d2, sink=sink)
+        trace["compute"] = ev(); trace["compute"].record()
+        sink.wait()
         torch.cuda.current_stream().synchronize()
 
     e2e_step()
@@ -482,6 +536,9 @@ def run_gpu_dist(args, dev, rank, world, local):
     q1.record()
     barrier()
     e2e_ms = q0.elapsed_time(q1)
+    print("rank %d e2e timeline (last step, ms from start): compute done %.1f, copies done %s" % (
+        rank, trace["start"].elapsed_time(trace["compute"]),
+        {kk: round(trace["start"].elapsed_time(e), 1) for kk, e in sink.done.items()}), file=sys.stderr, flush=True)
 
     t = torch.tensor([ms, e2e_ms, float(h2d), float(d2h), float(launches)], dtype=torch.float64, device=tdev)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -512,7 +569,7 @@ def run_gpu_dist(args, dev, rank, world, local):
                        "useful_tflop_per_step": fl["total"] / 1e12, "seconds_per_pipeline": ms_step * 1e-3},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(tsum[2]), "d2h_bytes_per_step": int(tsum[3]),
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "note": "edge arrays H2D on every rank; each rank's rows of C1 and S (and C2hat^T on rank 0) D2H into pinned memory"},
+                    "note": "edge arrays H2D on every rank; each rank's rows of C1, S and C2hat D2H into pinned memory (sum over ranks = the three full matrices)"},
             "gpu_launches": int(tsum[4]),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",

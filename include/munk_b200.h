@@ -145,6 +145,13 @@ int munk_transpose_lower(int n, const double* W, long ldw, double* C, long ldc, 
 int munk_download_upper(int n, const double* C, long ldc, double* host, long ldh, int row_block,
                         void* stream);
 
+/* Device -> host copy of a rows x cols block (both row-major, leading dimensions in elements):
+ * one strided DMA, asynchronous on `stream` when `host` is page-locked.  The multi-GPU result
+ * path uses it to move only the non-zero part of each rank's rows of the triangular factor
+ * (the array saved at scripts/compute_embeddings.py:72). */
+int munk_download_block(int rows, int cols, const double* C, long ldc, double* host, long ldh,
+                        void* stream);
+
 /* out[g][:] = mean of in[members[gptr[g] .. gptr[g+1])][:]; used to fold duplicated source
  * landmarks (np.linalg.pinv's minimum-norm least-squares answer, munk/munk/munk.py:109). */
 int munk_group_mean_rows(int ngroups, const int* gptr, const int* members, int ncols,

@@ -213,6 +213,21 @@ int munk_download_upper(int n, const double* C, long ldc, double* host, long ldh
   return MUNK_OK;
 }
 
+int munk_download_block(int rows, int cols, const double* C, long ldc, double* host, long ldh,
+                        void* stream) {
+  if (rows < 0) return -1;
+  if (cols < 0) return -2;
+  if (rows == 0 || cols == 0) return MUNK_OK;
+  if (!C) return -3;
+  if (ldc < cols) return -4;
+  if (!host) return -5;
+  if (ldh < cols) return -6;
+  MUNK_CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)ldh * sizeof(double), C, (size_t)ldc * sizeof(double),
+                                  (size_t)cols * sizeof(double), (size_t)rows,
+                                  cudaMemcpyDeviceToHost, S(stream)));
+  return MUNK_OK;
+}
+
 int munk_copy_lower(int n, const double* in, long ldi, double* out, long ldo, void* stream) {
   return copy_lower(n, in, ldi, out, ldo, S(stream));
 }

@@ -185,6 +185,14 @@ class Device:
         check(lib.munk_download_upper(n, _ptr(C), C.stride(0), host.data_ptr(), host.stride(0),
                                       row_block, self.stream()), "munk_download_upper")
 
+    def download_block(self, src, host):
+        """host (CPU view, unit column stride) <- src (CUDA view of the same shape, unit column
+        stride): one strided DMA on the current stream, asynchronous if `host` is pinned."""
+        assert host.device.type == "cpu" and host.dtype == torch.float64 and src.shape == host.shape
+        assert host.dim() == 2 and (host.shape[1] <= 1 or (host.stride(1) == 1 and src.stride(1) == 1))
+        check(lib.munk_download_block(host.shape[0], host.shape[1], _ptr(src), src.stride(0),
+                                      host.data_ptr(), host.stride(0), self.stream()), "munk_download_block")
+
     def group_mean_rows(self, B, ncols, gptr, members):
         g = len(gptr) - 1
         out = self.empty(g, ncols)
@@ -311,8 +319,9 @@ class Device:
                                    _ptr(stair_n) if stair_n is not None else None, row0, k0,
                                    self.stream()), "munk_dgemm_stair")
 
-    def transpose(self, X, rows, cols):
-        out = self.empty(cols, rows)
+    def transpose(self, X, rows, cols, out=None):
+        """out (cols x rows) = X[:rows, :cols]^T."""
+        out = self.empty(cols, rows) if out is None else out
         check(lib.munk_transpose(rows, cols, _ptr(X), X.stride(0), _ptr(out), out.stride(0),
                                  self.stream()), "munk_transpose")
         return out

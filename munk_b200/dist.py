@@ -1,7 +1,7 @@
 """Multi-GPU MUNK pipeline: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch).
 
-Process grid.  The factorisations use a 1 x P block-column-cyclic layout (block width 512): block
-column j belongs to rank j mod P.  With NVSwitch every rank sees every peer at full bandwidth, so
+Process grid.  The factorisations use a 1 x P block-column-cyclic layout (block width 512) dealt
+in serpentine rounds (ranks 0..P-1, then P-1..0, ...; ColumnCyclic.owner).  With NVSwitch every rank sees every peer at full bandwidth, so
 the per-rank panel traffic of a P_r x P_c grid (the whole panel, n^2/2 doubles in total) is the
 same for any grid shape; 1 x P keeps each panel's factorisation on one GPU (no intra-panel
 exchange) and leaves every rank with the complete factor L, which is what the later stages want:
@@ -42,13 +42,18 @@ class ColumnCyclic:
         self.nblk = (self.n + self.nb - 1) // self.nb
 
     def owner(self, j):
-        return j % self.world
+        """Serpentine rounds (0 .. P-1, P-1 .. 0, 0 .. P-1, ...): the work attached to a block
+        column (trailing updates, the staircase solve, the k-range of its score rows) shrinks
+        linearly with j, and plain round-robin would give rank 0 the heaviest block of every
+        round (measured at 8 GPUs: 28 ms vs 20 ms in the score product)."""
+        r, rnd = j % self.world, j // self.world
+        return r if rnd % 2 == 0 else self.world - 1 - r
 
     def cols(self, j):
         return j * self.nb, min(self.n, (j + 1) * self.nb)
 
     def blocks_of(self, rank):
-        return list(range(rank, self.nblk, self.world))
+        return [j for j in range(self.nblk) if self.owner(j) == rank]
 
     def rows_of(self, rank):
         """Global row indices (of C1 / S) owned by `rank`, ascending."""
@@ -234,9 +239,84 @@ def staircase_rhs(n, owned_cols, landmark_cols, device):
     return X, torch.from_numpy(stair).to(device), n_own_pad
 
 
+class ShardSink:
+    """Pinned host buffers for one rank's share of the three results and a copy stream: its rows
+    of C1 and S (ColumnCyclic.rows_of(rank)) and its rows of C2hat, i.e. the column block
+    [col0, col1) of the replicated P = C2hat^T, so that every result leaves the box sharded and
+    no rank moves more than (n1 + 2 n2) n1 / P doubles.  Reusable across calls."""
+
+    def __init__(self, dev, n1, n2, rank, world):
+        self.dev, self.n1, self.n2 = dev, n1, n2
+        self.rows = ColumnCyclic(n1, world).rows_of(rank)
+        per = (n2 + world - 1) // world
+        self.col0, self.col1 = min(n2, rank * per), min(n2, (rank + 1) * per)
+        m = len(self.rows)
+        opts = dict(dtype=torch.float64, pin_memory=True)
+        self.C1 = torch.zeros((m, n1), **opts)       # C1 is upper triangular: the part left of each
+        self.blocks, l0 = [], 0                      # block's first column stays zero, never copied
+        cc = ColumnCyclic(n1, world)
+        for j in cc.blocks_of(rank):
+            a, b = cc.cols(j)
+            self.blocks.append((l0, l0 + b - a, a))
+            l0 += b - a
+        self.S = torch.empty((m, n2), **opts)
+        self.C2hat = torch.empty((self.col1 - self.col0, n1), **opts)
+        self.stream = torch.cuda.Stream(device=dev.index)
+        self.done = {}                     # name -> event recorded after that copy (timelines)
+
+    def _copy_out(self, name, host, src):
+        """host <- src (contiguous CUDA tensor produced on the current stream), on the copy stream.
+        Only the DMA runs there: anything that needs SMs (the transposes below) is enqueued on the
+        compute stream *before* the next GEMM, because a kernel on a second stream does not get
+        an SM while a tensor-core launch with long tiles occupies them all (measured: the copies
+        were delayed to the end of the score product)."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev.index))
+        with torch.cuda.stream(self.stream):
+            host.copy_(src, non_blocking=True)
+            self.done[name] = torch.cuda.Event(enable_timing=True)
+            self.done[name].record()
+        src.record_stream(self.stream)
+
+    def _transposed(self, X, rows, cols):
+        T = torch.empty((cols, rows), dtype=torch.float64, device=self.dev.torch_device)
+        return self.dev.transpose(X, rows, cols, out=T)
+
+    def push_C1(self, X, m_own):
+        """Rows of C1 = the first m_own columns of the solve result X (n1 x ...), transposed."""
+        if not m_own:
+            return
+        T = self._transposed(X, self.n1, m_own)
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev.index))
+        with torch.cuda.stream(self.stream):
+            for l0, l1, c0 in self.blocks:       # rows of block column c0.. are zero left of c0
+                self.dev.download_block(T[l0:l1, c0:], self.C1[l0:l1, c0:])
+            self.done["C1"] = torch.cuda.Event(enable_timing=True)
+            self.done["C1"].record()
+        T.record_stream(self.stream)
+
+    def push_P(self, P):
+        if self.col1 > self.col0:
+            self._copy_out("C2hat", self.C2hat, self._transposed(P[:, self.col0:], self.n1, self.col1 - self.col0))
+
+    def push_S(self, S, r0, r1):
+        """Local rows [r0, r1) of the rank's score rows."""
+        if r1 > r0:
+            src = S[r0:r1, :self.n2]
+            self._copy_out("S", self.S[r0:r1], src if src.is_contiguous() else src.contiguous())
+
+    def d2h_bytes(self):
+        c1 = sum((l1 - l0) * (self.n1 - c0) for l0, l1, c0 in self.blocks)
+        return (c1 + self.S.numel() + self.C2hat.numel()) * 8
+
+    def wait(self):
+        self.stream.synchronize()
+
+
 def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, group=None,
-                      src_lam=0.05, tgt_lam=0.05, homolog_idxs=None, marks=None):
-    """The whole hot path on `world` GPUs.  Returns a dict with the rank's shard:
+                      src_lam=0.05, tgt_lam=0.05, homolog_idxs=None, marks=None, sink=None):
+    """The whole hot path on `world` GPUs.  Returns a dict with the rank's shard
+    (`sink`: optional ShardSink; each result is copied to pinned host memory as soon as it is
+    enqueued, overlapping the remaining stages):
        rows   global row indices of C1 / S owned by this rank
        C1     (len(rows), n1) rows of the source embedding       (CUDA tensor)
        P      (n1, n2) C2hat^T, replicated                        (CUDA tensor, padded ld)
@@ -305,13 +385,24 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
     # enqueuing) and inspected once at the end of the step
     flags = torch.cat([dev.potrf_info_async(), dev2.potrf_info_async()]).to(torch.int64)
     P = dev.project(Q1, n1, B, n2, (gptr, members))
+    if sink is not None:
+        sink.push_C1(X, len(rows))
+        sink.push_P(P)
 
     mark("embed")
     # 4. my rows of S = C1 C2hat^T:  S_r = X_own^T P, k-range clipped by the same staircase
     m_own = len(rows)
     S = dev.empty(max(m_own, 1), n2)
-    if m_own:
+    if m_own and sink is None:
         dev.gemm_stair(MC, MC, m_own, n2, n1, 1.0, X, P, 0.0, S, 0, stair_m=stair, k0=0)
+    elif m_own:
+        # row blocks, bottom-up, each copied out while the next one is computed
+        from .pipeline import streamed_row_blocks
+        for t0, t1 in streamed_row_blocks((m_own + 127) // 128, (n2 + 127) // 128):
+            r0, r1 = t0 * 128, min(m_own, t1 * 128)
+            dev.gemm_stair(MC, MC, r1 - r0, n2, n1, 1.0, X[:, r0:], P, 0.0, S[r0:], 0,
+                           stair_m=stair[t0:t1], k0=0)
+            sink.push_S(S, r0, r1)
     C1 = X[:, :m_own].t() if m_own else X[:, :0].t()            # (m_own, n1) view of the solve
 
     mark("score")
@@ -322,6 +413,7 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
     if bad:
         from .device import NotPositiveDefinite
         raise NotPositiveDefinite("matrix is not positive definite (pivot %d)" % (bad - 1))
+    mark("flag_check")
     out = dict(rows=rows, C1=C1, P=P, S=S[:m_own], n1=n1, n2=n2)
     if homolog_idxs is not None:
         out["stats"] = dist_score_means(dev, S, rows, n1, n2, landmark_idxs, homolog_idxs, world, group)

@@ -135,6 +135,20 @@ class HostSink:
         return self.C1.numpy(), self.P.numpy().T, self.S.numpy()
 
 
+def streamed_row_blocks(tiles, col_tiles, cuts=(0.04, 0.12, 0.3, 0.6)):
+    """Row-tile ranges [(t0, t1), ...] of a score product whose blocks are copied out while the
+    next one is computed, in launch order: bottom block first, a thin top block last (`cuts` =
+    boundaries as fractions of the row tiles).  The top rows of the triangular factor contract
+    over the longest k-range, so the last launch is long and its own copy short.  The thin block
+    has equal-length tiles; its height is nudged so that they fill whole waves of SMs."""
+    edges = {0, tiles} | {min(tiles, max(0, int(round(c * tiles)))) for c in cuts[1:]}
+    want = max(1, int(round(cuts[0] * tiles)))
+    thin = min(range(max(1, want - 2), want + 3),
+               key=lambda t: (-(t * col_tiles) % B200_SMS) / float(t * col_tiles))
+    edges = sorted(edges | {min(tiles, thin)})
+    return list(reversed(list(zip(edges[:-1], edges[1:]))))
+
+
 class DeviceEmbedding:
     """Result of embed_device(): everything still on the GPU."""
 
@@ -159,14 +173,8 @@ class DeviceEmbedding:
         dev, n1, n2 = self.dev, self.n1, self.n2
         S = dev.empty(n1, n2)
         tiles = (n1 + 127) // 128
-        edges = {0, tiles} | {min(tiles, max(0, int(round(c * tiles)))) for c in cuts[1:]}
-        # the thin last block has equal-length tiles: pick its height so they fill whole waves
-        col_tiles, want = (n2 + 127) // 128, max(1, int(round(cuts[0] * tiles)))
-        thin = min(range(max(1, want - 2), want + 3),
-                   key=lambda t: (-(t * col_tiles) % B200_SMS) / float(t * col_tiles))
-        edges = sorted(edges | {min(tiles, thin)})
         stair_all = dev.ints([128 * t for t in range(tiles)])
-        for t0, t1 in reversed(list(zip(edges[:-1], edges[1:]))):
+        for t0, t1 in streamed_row_blocks(tiles, (n2 + 127) // 128, cuts):
             r0, r1 = t0 * 128, min(n1, t1 * 128)
             dev.gemm_stair(MC, MC, r1 - r0, n2, n1, 1.0, self.W1[:, r0:], self.P, 0.0, S[r0:], 0,
                            stair_m=stair_all[t0:t1], k0=0)

@@ -74,11 +74,17 @@ def test_column_cyclic_map():
     from munk_b200.dist import ColumnCyclic
     cc = ColumnCyclic(2000, 3, nb=512)
     assert cc.nblk == 4 and cc.cols(3) == (1536, 2000)
-    assert [cc.owner(j) for j in range(4)] == [0, 1, 2, 0]
-    assert cc.blocks_of(0) == [0, 3] and cc.blocks_of(2) == [2]
+    # serpentine rounds: 0 1 2 | 2 1 0 | 0 1 2 ... (balances work that shrinks with the block index)
+    assert [cc.owner(j) for j in range(4)] == [0, 1, 2, 2]
+    assert cc.blocks_of(0) == [0] and cc.blocks_of(2) == [2, 3]
     rows = sorted(sum((cc.rows_of(r) for r in range(3)), []))
     assert rows == list(range(2000))
-    assert cc.rows_of(0) == list(range(512)) + list(range(1536, 2000))
+    assert cc.rows_of(2) == list(range(1024, 2000))
+    big = ColumnCyclic(20000, 8)
+    assert [big.owner(j) for j in range(18)] == [0, 1, 2, 3, 4, 5, 6, 7, 7, 6, 5, 4, 3, 2, 1, 0, 0, 1]
+    assert sorted(sum((big.blocks_of(r) for r in range(8)), [])) == list(range(big.nblk))
+    load = [sum(20000 - big.cols(j)[0] for j in big.blocks_of(r)) for r in range(8)]
+    assert max(load) < 1.1 * min(load)
 
 
 def test_staircase_rhs_layout():

@@ -73,6 +73,24 @@ if rank == 0:
         world, n1, n2, k, err, err_stats, "OK" if ok else "FAIL"), flush=True)
     del emb, S_one
 
+# host shards through a ShardSink: bit-identical to the device results of the same call
+sink = mdist.ShardSink(dev, n1, n2, rank, world)
+o2 = mdist.dist_embed_scores(dev, n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"], rank, world,
+                             sink=sink)
+sink.wait()
+torch.cuda.synchronize()
+same = (torch.equal(sink.C1, o2["C1"].cpu()) and torch.equal(sink.S, o2["S"][:, :n2].cpu())
+        and torch.equal(sink.C2hat, o2["P"][:, sink.col0:sink.col1].t().cpu())
+        and sink.rows == o2["rows"])
+flag = torch.tensor([0 if same else 1], device=dev.torch_device)
+if world > 1:
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print("ShardSink host shards equal the device results on every rank: %s" % ("OK" if int(flag) == 0 else "FAIL"),
+          flush=True)
+ok = ok and int(flag) == 0
+del o2
+
 # timing
 for _ in range(2):
     run()
