@@ -130,3 +130,19 @@ def test_cli_flag_surface_matches_reference():
                  "--random_seed", "--src_lam", "--tgt_lam"):
         assert re.search(r"'%s'" % re.escape(flag), src), flag
     assert "default=400" in src and "default=28791" in src and src.count("default=0.05") == 2
+
+
+@pytest.mark.parametrize("n1,n2", [(20000, 16000), (16000, 6000), (1500, 900), (100, 120), (50000, 40000),
+                                   (129, 1), (2500, 16000)])
+def test_streamed_row_blocks_partition_bottom_up(n1, n2):
+    """Launch schedule of the streamed score product: every 128-row tile exactly once, bottom
+    block first, the thin top block last."""
+    from munk_b200.pipeline import streamed_row_blocks
+    tiles, col_tiles = (n1 + 127) // 128, (n2 + 127) // 128
+    blocks = streamed_row_blocks(tiles, col_tiles)
+    assert blocks[0][1] == tiles and blocks[-1][0] == 0
+    assert all(a < b for a, b in blocks)
+    assert all(prev[0] == nxt[1] for prev, nxt in zip(blocks[:-1], blocks[1:]))   # contiguous, descending
+    if tiles >= 25:
+        assert blocks[-1][1] - blocks[-1][0] == min(b - a for a, b in blocks)     # the last one is the thin one
+        assert blocks[-1][1] <= 0.04 * tiles + 3
