@@ -420,6 +420,60 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
     return out
 
 
+def gather_rows(local, n_rows, rank, world, group=None, dst=0):
+    """Row-sharded (len(rows_of(rank)) x ncols) CUDA tensors -> the full (n_rows x ncols) matrix in
+    global row order on rank `dst` (None elsewhere).  One NCCL gather of zero-padded shards."""
+    cc = ColumnCyclic(n_rows, world)
+    rows_by_rank = [cc.rows_of(r) for r in range(world)]
+    ncols = int(local.shape[1])
+    if world == 1:
+        return local[:, :ncols].contiguous()
+    mx = max(len(r) for r in rows_by_rank)
+    pad = torch.zeros((mx, ncols), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, parts, dst=_global_rank(group, dst), group=group)
+    if rank != dst:
+        return None
+    full = torch.empty((n_rows, ncols), dtype=local.dtype, device=local.device)
+    for r, rows in enumerate(rows_by_rank):
+        if rows:
+            full[torch.as_tensor(rows, device=local.device)] = parts[r][:len(rows)]
+    return full
+
+
+def embed_and_score_distributed(dev, inputs, rank, world, src_lam=0.05, tgt_lam=0.05, group=None):
+    """pipeline.embed_and_score on `world` GPUs (scripts/compute_embeddings.py under torchrun):
+    every rank runs dist_embed_scores on the same index inputs, the row shards of C1 and S are
+    gathered on rank 0 over NVLink and rank 0 returns the same dict as the single-GPU call
+    (host arrays, reference layouts); the other ranks return None."""
+    import time
+    inp = inputs
+    n1, n2 = len(inp["source_nodes"]), len(inp["target_nodes"])
+    marks = []
+    t0 = time.time()
+    out = dist_embed_scores(dev, n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"], rank, world,
+                            group=group, src_lam=src_lam, tgt_lam=tgt_lam, marks=marks)
+    torch.cuda.current_stream(dev.index).synchronize()
+    phase = {name: a.elapsed_time(b) * 1e-3 for (_, a), (name, b) in zip(marks[:-1], marks[1:])}
+    C1 = gather_rows(out["C1"].contiguous(), n1, rank, world, group)
+    S = gather_rows(out["S"][:, :n2].contiguous(), n1, rank, world, group)
+    if rank != 0:
+        return None
+    source_X = dev.download(C1, n1, n1)
+    target_X = dev.download(out["P"], n1, n2).T        # (n2, n1) transposed view, munk.py:109-110
+    scores = dev.download(S, n1, n2)
+    # the reference's four timer keys (munk.py:161-164) mapped onto the distributed phases: both
+    # Cholesky chains run interleaved in the first, the W-column solves are the factorisation
+    runtimes = dict(source_regularized_laplacian_runtime=phase.get("potrf_src", 0.0),
+                    source_rkhs_factorization_runtime=phase.get("solve_src", 0.0),
+                    target_regularized_laplacian_runtime=0.0,
+                    embed_runtime=phase.get("embed", 0.0))
+    return dict(source_X=source_X, target_X=target_X, scores=scores, source_nodes=inp["source_nodes"],
+                target_nodes=inp["target_nodes"], landmarks=inp["landmark_homs"], runtimes=runtimes,
+                score_runtime=phase.get("score", 0.0), wall=time.time() - t0)
+
+
 def dist_score_means(dev, S_local, rows, n1, n2, landmark_idxs, homolog_idxs, world, group=None):
     """mean(H_H), mean(other), difference over the row-sharded score matrix: local partial sums
     (munk_separate_scores_means on the local rows) + one all-reduce of 4 doubles."""

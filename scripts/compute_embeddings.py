@@ -7,7 +7,9 @@ map) runs on arrays (munk_b200.ingest, bit-exact with the reference's networkx p
 --networkx_ingest to use networkx itself); the numeric work (both regularized-Laplacian kernels,
 the source RKHS factor, the landmark projection and the n1 x n2 score product) runs in one
 device-resident pass (munk_b200.pipeline.embed_and_score); the three result matrices stream back
-to the host while later stages are still computing.
+to the host while later stages are still computing.  Launched under torchrun
+(`python -m torch.distributed.run --nproc-per-node N scripts/compute_embeddings.py ...`) the same
+pass is sharded over N GPUs and rank 0 writes the files.
 """
 import argparse
 import json
@@ -63,6 +65,22 @@ def run(args):
     log = munk.io.get_logger()
     random.seed(args.random_seed)   # accepted for compatibility; landmarks are the first k pairs
 
+    # Multi-GPU is opt-in: launched under torchrun (WORLD_SIZE > 1) the pipeline is sharded over
+    # the ranks (munk_b200.dist) and rank 0 writes the same files; a plain `python` launch is the
+    # single-GPU drop-in.
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank, local = int(os.environ.get('RANK', '0')), int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import logging
+        import torch
+        import torch.distributed as tdist
+        from munk_b200 import dist as mdist
+        from munk_b200.device import Device
+        torch.cuda.set_device(local)
+        tdist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        if rank != 0:
+            log.setLevel(logging.WARNING)
+
     log.info('Loading homologs list from %s', args.homolog_list)
     raw_homologs = util.read_homolog_list(args.homolog_list)
     load = load_with_networkx if args.networkx_ingest else load_with_arrays
@@ -74,9 +92,17 @@ def run(args):
     inputs = pipeline.index_inputs(source_nodes, source_edges, target_nodes, target_edges, homologs,
                                    args.n_landmarks)
     started = time.time()
-    res = pipeline.embed_and_score(None, None, homologs, args.n_landmarks, src_lam=args.src_lam,
-                                   tgt_lam=args.tgt_lam, inputs=inputs)
+    if world > 1:
+        res = mdist.embed_and_score_distributed(Device(local), inputs, rank, world,
+                                                src_lam=args.src_lam, tgt_lam=args.tgt_lam)
+    else:
+        res = pipeline.embed_and_score(None, None, homologs, args.n_landmarks, src_lam=args.src_lam,
+                                       tgt_lam=args.tgt_lam, inputs=inputs)
     total_time = time.time() - started
+    if res is None:                 # ranks > 0 of a torchrun launch: rank 0 writes the files
+        tdist.barrier()
+        tdist.destroy_process_group()
+        return
     landmarks = res['landmarks']
 
     log.info('Saving source species embeddings to %s', args.source_output_file)
@@ -101,6 +127,9 @@ def run(args):
         json.dump(dict(n_source_nodes=len(source_nodes), n_target_nodes=len(target_nodes),
                        runtimes=res['runtimes'], total_time=total_time), out, indent=2)
     log.info('MUNK embedding complete!')
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
 
 
 if __name__ == '__main__':
