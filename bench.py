@@ -336,7 +336,6 @@ def run_gpu(args):
     # ---- timed: e2e (host buffers in, pinned host results out, every step)
     h_e1 = [torch.from_numpy(x).pin_memory() for x in inp["edges1"]]
     h_e2 = [torch.from_numpy(x).pin_memory() for x in inp["edges2"]]
-    import numpy as np
     # The public device API (what scripts/compute_embeddings.py calls): host edge/index arrays in,
     # C1, C2hat^T and S streamed to the pinned buffers of a HostSink while later stages compute.
     sink = pipeline.HostSink(dev, n1, n2)

@@ -10,7 +10,6 @@ the host between the stages:
 """
 import time
 
-import numpy as np
 import torch
 
 from . import util
