@@ -43,20 +43,56 @@ __global__ void __launch_bounds__(256) separate_scores_kernel(const SepArgs a) {
   double* __restrict__ o_lloff = a.out_lloff + a.off_lloff[i];
   double* __restrict__ o_lnonl = a.out_lnonl + a.off_lnonl[i];
   double* __restrict__ o_other = a.out_other + a.off_other[i];
-  // Fast path — a non-landmark row without homolog cells (all but ~k + H of the n1 rows): every
-  // element goes to "other" (non-landmark column) or "landmark x non-landmark" (landmark
-  // column); two elements per thread with 16-byte loads.
-  if (!rl && hlo == hhi && (a.lds & 1) == 0 && (a.n2 & 1) == 0 && ((uintptr_t)a.S & 15) == 0) {
+  // Fast path — every non-landmark row (all but k of the n1 rows), four columns per thread
+  // iteration: two 16-byte loads of S, one 4-byte load of the four column flags and one of the
+  // rank of the first column.  A chunk without a landmark column and without a homolog cell
+  // (~97 % of them) is one contiguous 32-byte piece of "other", shifted by the rank and by the
+  // homolog cells before it; the rest go element by element.
+  if (!rl && (a.lds & 1) == 0 && (a.n2 & 3) == 0 && ((uintptr_t)a.S & 15) == 0 &&
+      ((uintptr_t)a.colL & 3) == 0) {
     const double2* __restrict__ row2 = reinterpret_cast<const double2*>(row);
-    const uchar2* __restrict__ cl2 = reinterpret_cast<const uchar2*>(a.colL);
-    const int2* __restrict__ rk2 = reinterpret_cast<const int2*>(a.colrank);
-    for (int p = blockIdx.y * blockDim.x + threadIdx.x; p < (a.n2 >> 1); p += gridDim.y * blockDim.x) {
-      const double2 v = row2[p];
-      const uchar2 cl = cl2[p];
-      const int2 rk = rk2[p];
-      const int j = 2 * p;
-      if (cl.x) o_lnonl[rk.x] = v.x; else o_other[j - rk.x] = v.x;
-      if (cl.y) o_lnonl[rk.y] = v.y; else o_other[j + 1 - rk.y] = v.y;
+    const unsigned* __restrict__ cl4 = reinterpret_cast<const unsigned*>(a.colL);
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < (a.n2 >> 2); c += gridDim.y * blockDim.x) {
+      const double2 v0 = row2[2 * c], v1 = row2[2 * c + 1];
+      const unsigned fl = cl4[c];
+      const int j = 4 * c;
+      const int rk = a.colrank[j];
+      int hb = 0;                    // homolog cells of this row in non-landmark columns < j
+      int hq = hlo;                  // first homolog cell with column >= j
+      for (; hq < hhi; ++hq) {
+        const int hc = a.h_col[hq];
+        if (hc >= j) break;
+        if (!a.colL[hc]) ++hb;
+      }
+      const bool hin = hq < hhi && a.h_col[hq] < j + 4;
+      if (fl == 0u && !hin) {
+        double* d = o_other + (j - rk - hb);
+        if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+          reinterpret_cast<double2*>(d)[0] = v0;
+          reinterpret_cast<double2*>(d)[1] = v1;
+        } else {
+          d[0] = v0.x;
+          *reinterpret_cast<double2*>(d + 1) = make_double2(v0.y, v1.x);
+          d[3] = v1.y;
+        }
+      } else {
+        const double vv[4] = {v0.x, v0.y, v1.x, v1.y};
+        int r = rk;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = j + e;
+          const bool is_h = hq < hhi && a.h_col[hq] == col;
+          if (is_h) ++hq;
+          if ((fl >> (8 * e)) & 0xffu) {
+            o_lnonl[r] = vv[e];          // other row, landmark column (homolog cell or not)
+            ++r;
+          } else if (is_h) {
+            ++hb;                        // a homolog cell: not in "other", shifts what follows
+          } else {
+            o_other[col - r - hb] = vv[e];
+          }
+        }
+      }
     }
     return;
   }
@@ -161,7 +197,9 @@ extern "C" int munk_separate_scores(int n1, int n2, const double* S, long lds,
   if (n1 <= 0 || n2 <= 0) return MUNK_OK;
   SepArgs a{n1, n2, S, lds, rowL, colL, colrank, p_ptr, p_col, h_ptr, h_col,
             off_lloff, off_lnonl, off_other, out_lloff, out_lnonl, out_other};
-  dim3 grid(n1, (unsigned)std::min(8, (n2 + 255) / 256));
+  // two blocks per row: each thread streams >= 8 four-column chunks at C3 size, which amortises
+  // the per-row set-up (flags, CSR pointers, output offsets) the old 8-way split paid per block
+  dim3 grid(n1, (unsigned)std::max(1, std::min(2, (n2 + 2047) / 2048)));
   separate_scores_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   MUNK_CUDA_TRY(cudaGetLastError());
   return MUNK_OK;

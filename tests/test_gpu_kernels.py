@@ -298,3 +298,22 @@ def test_random_network_generator(dev):
     res = permtest.run_permutation_test(seed_G, seed_G, [(n, n) for n in data["nodes"][:40]], 10,
                                         n_permutations=3, mode="graphs", seed=1)
     assert res["errs"] == 0 and len(res["random"]["mean_diffs"]) == 3
+
+
+@pytest.mark.parametrize("n1,n2,seed", [(37, 40, 0), (64, 52, 1), (50, 30, 2), (300, 2052, 3), (9, 4, 4),
+                                        (120, 4096, 5)])
+def test_separate_scores_random_cells_exact(dev, n1, n2, seed):
+    """separate_scores against the oracle on random index lists: repeated landmarks, one-to-many
+    homologs, homolog cells inside landmark columns and several per four-column chunk, row lengths
+    that do and do not take the vectorised path.  Exact, in order."""
+    import munk_b200 as m
+    rng = np.random.default_rng(seed)
+    k = int(rng.integers(1, min(n1, n2, 12) + 1))
+    ls, lt = rng.choice(n1, k, replace=True), rng.choice(n2, k, replace=True)
+    extra = int(rng.integers(k, 6 * k + 8))
+    hs = np.concatenate([ls, rng.choice(n1, extra)])
+    ht = np.concatenate([lt, rng.choice(max(1, n2 // 3), extra)])          # crowded columns
+    l_idx, h_idx = list(zip(ls.tolist(), lt.tolist())), list(zip(hs.tolist(), ht.tolist()))
+    S = rng.random((n1, n2))
+    for got, want in zip(m.separate_scores(S, l_idx, h_idx), oracle.separate_scores(S, l_idx, h_idx)):
+        assert np.array_equal(got, want)
