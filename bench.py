@@ -166,7 +166,10 @@ def cpu_info():
 
 
 def cpu_sample(cfg_name, n1, n2, reps=1):
-    """Times the CPU port on an (n1, n2) sample of the workload; returns (TFLOP/s, description)."""
+    """Times the CPU port on an (n1, n2) sample of the workload (never larger than the
+    configuration itself); returns (TFLOP/s, seconds, description)."""
+    from munk_b200 import synthetic
+    n1, n2 = min(n1, synthetic.CONFIGS[cfg_name][0]), min(n2, synthetic.CONFIGS[cfg_name][1])
     _, _, k, _, (G1, G2, homs) = make_inputs(cfg_name, 0, n1, n2)
     best = min(cpu_pipeline(G1, G2, homs, k)[0] for _ in range(reps))
     fl = pipeline_flops(n1, n2, k)["total"]
@@ -179,7 +182,9 @@ def run_reference(args):
     if rank != 0:
         return
     info = cpu_info()
-    n1, n2 = args.cpu_n1, args.cpu_n2
+    from munk_b200 import synthetic
+    n1 = min(args.cpu_n1, synthetic.CONFIGS[args.config][0])
+    n2 = min(args.cpu_n2, synthetic.CONFIGS[args.config][1])
     _, _, k, _, (G1, G2, homs) = make_inputs(args.config, 0, n1, n2)
     for _ in range(min(args.warmup, 1)):
         cpu_pipeline(G1, G2, homs, k)
