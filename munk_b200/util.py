@@ -5,10 +5,12 @@ sorted() over node names (util.py:86-87), homolog filtering keeps file order and
 (util.py:60-69).  simplify_graph / simple_two_core are restated for networkx >= 3, where
 connected_component_subgraphs and Graph.selfloop_edges (util.py:19,30) no longer exist.
 """
-import networkx as nx
 import numpy as np
 
 from .io import get_logger
+
+# networkx is imported where it is used (simplify_graph, simple_two_core): it costs ~0.7 s at
+# start-up and the array ingestion path of the CLI never touches it.
 
 
 def sorted_nodes(G):
@@ -50,6 +52,7 @@ def homologs_in_graphs(G1, G2, homologs):
 
 def simplify_graph(G, verbose=True):
     """Largest connected component (first one of maximal size), then self loops removed."""
+    import networkx as nx
     log = get_logger()
     if not nx.is_connected(G):
         parts = [G.subgraph(nodes).copy() for nodes in nx.connected_components(G)]
@@ -68,6 +71,7 @@ def simplify_graph(G, verbose=True):
 
 def simple_two_core(G, verbose=True):
     """2-core of the simplified graph."""
+    import networkx as nx
     log = get_logger()
     G = simplify_graph(G, verbose)
     n_nodes, n_edges = G.number_of_nodes(), G.number_of_edges()
