@@ -70,6 +70,24 @@ def test_statistics_match_reference_formulae():
     assert a == b and sorted(a) == idx and a != permuted_homolog_idxs(idx, 4)
 
 
+def test_gather_rows_reassembles_global_order_gloo():
+    """dist.gather_rows: serpentine row shards of three ranks (one of them with a short last
+    block) come back in global row order on rank 0, nothing on the other ranks."""
+    outs = run_ranks("""
+        from munk_b200.dist import ColumnCyclic, gather_rows
+        n, ncols = 2500, 3                       # 5 blocks of 512 (last: 452 rows) over 3 ranks
+        rows = ColumnCyclic(n, world).rows_of(rank)
+        local = torch.tensor(rows, dtype=torch.float64)[:, None] * torch.tensor([1.0, 10.0, -1.0])
+        full = gather_rows(local, n, rank, world)
+        if rank == 0:
+            want = torch.arange(n, dtype=torch.float64)[:, None] * torch.tensor([1.0, 10.0, -1.0])
+            print("ok" if torch.equal(full, want) else "bad")
+        else:
+            print("none" if full is None else "bad")
+    """, world=3)
+    assert [o.strip() for o in outs] == ["ok", "none", "none"]
+
+
 def test_column_cyclic_map():
     from munk_b200.dist import ColumnCyclic
     cc = ColumnCyclic(2000, 3, nb=512)
