@@ -88,6 +88,37 @@ def test_gather_rows_reassembles_global_order_gloo():
     assert [o.strip() for o in outs] == ["ok", "none", "none"]
 
 
+def test_sharded_statistic_plans_add_up_to_the_oracle():
+    """dist._local_plan per rank (row flags, H_H cells, |other| of the rank's rows), evaluated with
+    numpy on the rank's rows of S and combined like dist_score_means' all-reduce, reproduces the
+    oracle's mean(H_H) and mean(other) over the whole matrix — with repeated landmarks, one-to-many
+    homologs and homolog cells inside landmark rows / columns."""
+    from munk_b200.dist import ColumnCyclic, _local_plan
+    from oracle import munk_oracle as oracle
+    rng = np.random.default_rng(11)
+    n1, n2, world, k = 1700, 260, 3, 12
+    ls, lt = rng.choice(n1, k, replace=True), rng.choice(n2, k, replace=True)
+    hs = np.concatenate([ls, rng.choice(n1, 90)])
+    ht = np.concatenate([lt, rng.choice(n2 // 4, 90)])
+    l_idx, h_idx = list(zip(ls.tolist(), lt.tolist())), list(zip(hs.tolist(), ht.tolist()))
+    S = rng.random((n1, n2))
+    sums = np.zeros(4)
+    for rank in range(world):
+        rows = ColumnCyclic(n1, world).rows_of(rank)
+        plan = _local_plan(len(rows), n2, rows, l_idx, h_idx)
+        S_loc = S[rows]
+        hh = S_loc[plan.h_row, plan.h_col]
+        keep = np.outer(plan.rowL == 0, plan.colL == 0)
+        other_mask = keep.copy()
+        other_mask[plan.h_row, plan.h_col] = False
+        assert int(other_mask.sum()) == plan.n_other and plan.n_hh == len(hh)
+        sums += [hh.sum(), plan.n_hh, S_loc[other_mask].sum(), plan.n_other]
+    want = oracle.separate_scores(S, l_idx, h_idx)
+    assert int(sums[1]) == len(want[3]) and int(sums[3]) == len(want[4])
+    assert abs(sums[0] / sums[1] - want[3].mean()) < 1e-12
+    assert abs(sums[2] / sums[3] - want[4].mean()) < 1e-12
+
+
 def test_column_cyclic_map():
     from munk_b200.dist import ColumnCyclic
     cc = ColumnCyclic(2000, 3, nb=512)
