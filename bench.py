@@ -15,10 +15,15 @@ BASELINE.json's 20k -> 16k configuration (C3); N>1 shards that one pipeline over
   e2e    = the same through the host-buffer API: edge/index arrays copied H2D every step and
            C1, C2hat and S copied back into pinned host memory inside the timed region.
   roofline     = the dominant kernel (the DMMA score GEMM launch) against the measured FP64 DMMA peak.
-  cpu_baseline = the CPU oracle (numpy/scipy port of the reference algorithm) on a bounded sample.
+  parity       = after the timed regions: the whole score matrix the timed steps produced (all ranks'
+                 shards at N>1) against an independent CPU computation (oracle.scores_by_cholesky).
+  api_e2e      = (N=1) munk.embed_networks + munk.scores from networkx graphs to host numpy arrays.
+  cpu_baseline = (N=1) the reference arm below on a bounded quarter-size sample, in a subprocess; plus
+                 the full-configuration time if `--impl reference` ran on this host before.
 
-`--impl reference` times the reference's CPU algorithm (oracle port: inv + eigh + pinv + dot via
-numpy/scipy with every host thread) on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref, installed by oracle/build_ref.py:
+munk.embed_networks + np.dot, i.e. inv + eigh + pinv + dot via numpy/scipy) on the same configuration
+with every host core, one step, without importing munk_b200.
 
 Diagnostics (stderr only): MUNK_BENCH_TRACE=1 prints per-step phase times and device-idle gaps of
 the multi-GPU run; MUNK_BENCH_CLOCK_PERIOD=<s> sets the clock sampling period.
@@ -35,7 +40,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "MUNK pipeline FP64 TFLOP/s (useful flops / end-to-end s), 20k->16k nodes"
+METRIC = "MUNK pipeline FP64 TFLOP/s (useful flops / pipeline s), 20k->16k nodes"
 UNIT = "TFLOP/s"
 # DRAM bytes (read + write) of the C3 score launch, ncu --set full, profiles/r01_ncu_summary.md
 NCU_SCORE_TRAFFIC_BYTES = 38.0e9
@@ -124,7 +129,8 @@ class ClockSampler(threading.Thread):
 
 
 def make_inputs(cfg_name, rank, n1=None, n2=None):
-    from munk_b200 import pipeline, synthetic
+    from munk_b200 import pipeline
+    import synth as synthetic
     c = synthetic.CONFIGS[cfg_name]
     n1, n2 = n1 or c[0], n2 or c[1]
     m, H, k = c[2], c[3], c[4]
@@ -143,67 +149,197 @@ def _settle_gc():
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_pipeline(G1, G2, homs, k):
-    """The reference algorithm (oracle port): embed_networks + np.dot."""
-    from oracle import munk_oracle as oracle
-    t0 = time.time()
-    out = oracle.embed_networks(G1, G2, homs, k)
-    S = oracle.scores(out["C1"], out["C2"])
-    return time.time() - t0, S
+# Nothing in this section imports munk_b200 (the reference arm must not map the repo's .so).
+def host_cores():
+    """Cores this process may run on (cgroup/affinity aware)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def force_host_threads():
+    """Every BLAS/OpenMP pool gets all host cores, whatever the launcher exported (torchrun sets
+    OMP_NUM_THREADS=1 when N>1).  Must run before numpy is imported."""
+    n = str(host_cores())
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = n
+
+
+def workload_name(cfg_name, n1, n2, k):
+    import synth
+    return "%s: source %d / target %d nodes, %d landmarks, lam 0.05, Barabasi-Albert m=%d (seeds 1/2)" % (
+        cfg_name, n1, n2, k, synth.CONFIGS[cfg_name][2])
 
 
 def cpu_info():
     import numpy, scipy
-    info = {"cores": os.cpu_count(), "numpy": numpy.__version__, "scipy": scipy.__version__}
+    info = {"cores": host_cores(), "os_cpu_count": os.cpu_count(), "numpy": numpy.__version__,
+            "scipy": scipy.__version__}
     try:
         from threadpoolctl import threadpool_info
         pools = threadpool_info()
         info["blas"] = ["%s %s x%d" % (p.get("internal_api"), p.get("version"), p.get("num_threads")) for p in pools]
         info["threads"] = max([p.get("num_threads", 1) for p in pools] + [1])
     except Exception:
-        info["threads"] = os.cpu_count()
+        info["threads"] = host_cores()
     return info
 
 
-def cpu_sample(cfg_name, n1, n2, reps=1):
-    """Times the CPU port on an (n1, n2) sample of the workload (never larger than the
-    configuration itself); returns (TFLOP/s, seconds, description)."""
-    from munk_b200 import synthetic
-    n1, n2 = min(n1, synthetic.CONFIGS[cfg_name][0]), min(n2, synthetic.CONFIGS[cfg_name][1])
-    _, _, k, _, (G1, G2, homs) = make_inputs(cfg_name, 0, n1, n2)
-    best = min(cpu_pipeline(G1, G2, homs, k)[0] for _ in range(reps))
-    fl = pipeline_flops(n1, n2, k)["total"]
-    return fl / best / 1e12, best, "oracle port (inv+eigh+pinv+dot) on %s-shaped sample n1=%d n2=%d k=%d: %.2f s" % (
-        cfg_name, n1, n2, k, best)
+def reference_callable():
+    """(kind, fn): fn(G1, G2, homs, k) -> (seconds, runtimes dict) runs the reference's public path
+    — munk.embed_networks (munk/munk/munk.py:114-176) followed by the score product
+    np.dot(source_X, target_X.T) (scripts/compute_embeddings.py:81).  kind "reference" = the
+    unmodified package pip-installed under oracle/_ref (oracle/build_ref.py); "port" = the oracle
+    restatement, used only if oracle/_ref is absent."""
+    import numpy as np
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is not None:
+        def run_ref(G1, G2, homs, k):
+            t0 = time.time()
+            (source_X, _), (target_X, _), _, runtimes = ref.embed_networks(G1, G2, homs, k)
+            t_embed = time.time() - t0
+            S = np.dot(source_X, target_X.T)                   # compute_embeddings.py:81
+            t = time.time() - t0
+            runtimes = dict(runtimes, score_product=t - t_embed, shape=list(S.shape))
+            return t, runtimes
+        return "reference", run_ref
+    from oracle import munk_oracle as oracle
+
+    def run_port(G1, G2, homs, k):
+        t0 = time.time()
+        out = oracle.embed_networks(G1, G2, homs, k)
+        t_embed = time.time() - t0
+        S = oracle.scores(out["C1"], out["C2"])
+        t = time.time() - t0
+        return t, {"embed_networks": t_embed, "score_product": t - t_embed, "shape": list(S.shape)}
+    return "port", run_port
+
+
+def ref_cache_path(cfg_name):
+    return os.path.join(ROOT, ".bench_cache", "reference_%s.json" % cfg_name)
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation on the SAME configuration as the
+    product arm (C3 by default: one step of ~5-8 minutes on 16-32 host cores, so steps = 1 and
+    warm-up = 0 whatever --steps/--warmup say; LAPACK has no JIT to warm).  A calibration run on a
+    quarter-size sample (n^3 model) guards the driver's time limit: if the full configuration is
+    projected to exceed MUNK_REF_BUDGET_S (default 700 s) the largest same-shape sample that fits is
+    timed instead and the line says so (`config.same_config` false).  --ref-n1/--ref-n2 force a
+    sample (the bounded cpu_baseline leg of the product arm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    info = cpu_info()
-    from munk_b200 import synthetic
-    n1 = min(args.cpu_n1, synthetic.CONFIGS[args.config][0])
-    n2 = min(args.cpu_n2, synthetic.CONFIGS[args.config][1])
-    _, _, k, _, (G1, G2, homs) = make_inputs(args.config, 0, n1, n2)
-    for _ in range(min(args.warmup, 1)):
-        cpu_pipeline(G1, G2, homs, k)
-    times = [cpu_pipeline(G1, G2, homs, k)[0] for _ in range(max(1, min(args.steps, args.cpu_max_steps)))]
-    t = sum(times) / len(times)
+    import synth
+    from threadpoolctl import threadpool_limits
+    cores = host_cores()
+    n1c, n2c, m, H, k = synth.CONFIGS[args.config]
+    kind, run = reference_callable()
+    assert "munk_b200" not in sys.modules
+    budget = float(os.environ.get("MUNK_REF_BUDGET_S", "700"))
+    calibration = None
+    with threadpool_limits(limits=cores):
+        info = cpu_info()
+        if args.ref_n1:
+            n1, n2 = min(args.ref_n1, n1c), min(args.ref_n2 or args.ref_n1, n2c)
+        else:
+            G1, G2, homs = synth.make_case(240, 200, m, 60, seeds=(1, 2))
+            run(G1, G2, homs, 30)                       # imports, BLAS thread start-up
+            q1, q2 = max(200, n1c // 4), max(150, n2c // 4)
+            G1, G2, homs = synth.make_case(q1, q2, m, min(H, q1, q2), seeds=(1, 2))
+            t_cal, _ = run(G1, G2, homs, min(k, len(homs)))
+            est = t_cal * (n1c / q1) ** 3
+            calibration = {"n1": q1, "n2": q2, "seconds": t_cal, "projected_full_s": est, "budget_s": budget}
+            n1, n2 = n1c, n2c
+            if est > budget:
+                f = (budget / est) ** (1.0 / 3.0)
+                n1, n2 = max(q1, int(n1c * f) // 500 * 500), max(q2, int(n2c * f) // 500 * 500)
+        G1, G2, homs = synth.make_case(n1, n2, m, min(H, n1, n2), seeds=(1, 2))
+        k = min(k, len(homs))
+        t, runtimes = run(G1, G2, homs, k)
+        info = cpu_info()
+    same = (n1, n2) == (n1c, n2c)
     fl = pipeline_flops(n1, n2, k)["total"]
     val = fl / t / 1e12
-    sample = "oracle port of the reference algorithm on %s-shaped sample n1=%d n2=%d k=%d, %d timed steps" % (
-        args.config, n1, n2, k, len(times))
-    print(json.dumps({
+    what = ("unmodified reference (oracle/_ref: munk.embed_networks + np.dot, munk.py:114-176, "
+            "compute_embeddings.py:81)" if kind == "reference" else "oracle port of the reference algorithm")
+    sample = "%s on %s, %d threads: %.1f s" % (
+        what, ("the full configuration" if same else "a same-shape sample") + " n1=%d n2=%d k=%d" % (n1, n2, k),
+        info.get("threads", cores), t)
+    line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s sample %d/%d nodes, k=%d (Barabasi-Albert, seeds 1/2)" % (args.config, n1, n2, k),
-                   "note": "useful flops counted with the build's formulae so GPU/CPU ratios are time ratios"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": info.get("threads"), "kind": "port",
+        "steps": 1, "warmup": 0, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, n1, n2, k), "same_config": same,
+                   "parallelism": "CPU, %d BLAS threads" % info.get("threads", cores),
+                   "useful_tflop_per_step": fl / 1e12, "seconds_per_pipeline": t,
+                   "note": "value = the build's useful-flop count / reference seconds, so value ratios are time "
+                           "ratios; the reference's own algorithm executes ~88 TFLOP at C3 (inv + eigh + dense "
+                           "diag product + pinv + dot)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": info.get("threads", cores), "kind": kind,
                          "sample": sample, "host": info},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+        "reference_runtimes_s": runtimes, "calibration": calibration,
+    }
+    if same and not args.no_cache:
+        try:
+            import socket
+            os.makedirs(os.path.dirname(ref_cache_path(args.config)), exist_ok=True)
+            with open(ref_cache_path(args.config), "w") as f:
+                json.dump({"seconds": t, "value": val, "kind": kind, "cores": info.get("threads", cores),
+                           "host": socket.gethostname(), "when": time.time(), "n1": n1, "n2": n2, "k": k,
+                           "runtimes_s": runtimes}, f)
+        except OSError:
+            pass
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(cfg_name, n1, n2):
+    """The product arm's `cpu_baseline`: the reference arm on a bounded same-shape sample, run in a
+    subprocess (its own BLAS thread settings, no munk_b200 in that process), plus — when
+    `--impl reference` already ran the full configuration on this host (the driver runs it first) —
+    that full-size time under `full_config`."""
+    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", cfg_name,
+                          "--ref-n1", str(n1), "--ref-n2", str(n2), "--no-cache"],
+                         capture_output=True, text=True, timeout=1500,
+                         env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    out = None
+    for ln in res.stdout.splitlines():
+        if ln.startswith("{"):
+            out = json.loads(ln)
+    if out is None:
+        return {"value": None, "unit": UNIT, "cores": host_cores(), "kind": "port",
+                "sample": "cpu baseline leg failed: %s" % res.stderr[-300:]}
+    base = out["cpu_baseline"]
+    base["ms_per_step"] = out["ms_per_step"]
+    base["runtimes_s"] = out.get("reference_runtimes_s")
+    try:
+        import socket
+        full = json.load(open(ref_cache_path(cfg_name)))
+        if full.get("host") == socket.gethostname() and time.time() - full.get("when", 0) < 6 * 3600:
+            base["full_config"] = {"seconds": full["seconds"], "value": full["value"], "kind": full["kind"],
+                                   "cores": full["cores"], "runtimes_s": full.get("runtimes_s"),
+                                   "source": "bench.py --impl reference on this host, %.0f s ago" % (
+                                       time.time() - full["when"])}
+    except (OSError, ValueError, KeyError):
+        pass
+    return base
+
+
+def cpu_checker(n1, edges1, n2, edges2, landmark_idxs):
+    """Independent CPU scores for the `parity` object: oracle.scores_by_cholesky (LAPACK Cholesky
+    route, pinned to the reference's S in tests/test_oracle.py), all host cores."""
+    import numpy as np
+    from threadpoolctl import threadpool_limits
+    from oracle import munk_oracle as oracle
+    t0 = time.time()
+    with threadpool_limits(limits=host_cores()):
+        out = oracle.scores_by_cholesky(n1, np.stack(edges1, axis=1).astype(np.int64), n2,
+                                        np.stack(edges2, axis=1).astype(np.int64), landmark_idxs)
+    out["seconds"] = time.time() - t0
+    return out
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -226,6 +362,24 @@ def emit(line):
         sys.stdout.write(data.decode()); sys.stdout.flush()
     else:
         os.write(_JSON_FD, data)
+
+
+def parity_vs_checker(S_host, chk, landmark_idxs, what):
+    """max|S - S_cpu| / max|S_cpu| over the whole matrix (north_star tolerance 1e-8) plus the
+    interpolation property S[Ls,:] = D2[Lt,:] against the CPU's D2 rows, in row chunks."""
+    import numpy as np
+    S_ref = chk["S"]
+    scale = float(np.abs(S_ref).max())
+    err = 0.0
+    for r0 in range(0, S_ref.shape[0], 2048):
+        err = max(err, float(np.abs(S_host[r0:r0 + 2048] - S_ref[r0:r0 + 2048]).max()))
+    ls = [int(a) for a, _ in landmark_idxs]
+    interp = float(np.abs(S_host[ls, :] - chk["D2_rows"]).max())
+    return {"S_max_rel_err": err / scale, "S_landmark_rows_vs_cpu_D2_rows": interp / scale, "tolerance": 1e-8,
+            "ok": bool(err / scale <= 1e-8 and interp / scale <= 1e-8), "cells_compared": int(S_ref.size),
+            "what": what,
+            "checker": "oracle.scores_by_cholesky: CPU LAPACK Cholesky route, no GPU data; pinned to the "
+                       "reference's S in tests/test_oracle.py; %.1f s on %d host threads" % (chk["seconds"], host_cores())}
 
 
 def run_gpu(args):
@@ -365,6 +519,53 @@ def run_gpu(args):
     barrier()
     e2e_ms = q0.elapsed_time(q1)
 
+    # ---- parity (outside every timed region): the scores the timed steps left in S_buf, the host
+    # copy the e2e steps produced, and D1 1 = 1 through the factor, against an independent CPU run
+    parity = api = None
+    if rank == 0 and world == 1 and not args.no_parity:
+        import numpy as np
+        chk = cpu_checker(n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"])
+        parity = parity_vs_checker(dev.download(S_buf, n1, n2), chk, inp["landmark_idxs"],
+                                   "S of the last device-resident timed step, whole matrix")
+        e2e_par = parity_vs_checker(sink.S.numpy(), chk, inp["landmark_idxs"], "S in the e2e HostSink")
+        parity["e2e_S_max_rel_err"] = e2e_par["S_max_rel_err"]
+        W = torch.tril(A1[:, :n1])
+        ones = torch.ones(n1, dtype=torch.float64, device=tdev)
+        parity["D1_row_sums_minus_1_max"] = float((W.t().mv(W.mv(ones)) - 1.0).abs().max())
+        C1h = sink.C1.numpy()
+        ls_ = [int(a) for a, _ in inp["landmark_idxs"]]
+        # C1 C1[Ls,:]^T = D1[:,Ls] from the host copy of the factor (64 sampled landmark columns)
+        pick = ls_[:: max(1, len(ls_) // 64)]
+        parity["C1_C1t_landmark_cols_max_rel_err"] = float(
+            np.abs(C1h @ C1h[pick, :].T - chk["D1_cols"][:, [ls_.index(c) for c in pick]]).max()
+            / np.abs(chk["D1_cols"]).max())
+        parity["ok"] = bool(parity["ok"] and e2e_par["ok"] and parity["D1_row_sums_minus_1_max"] < 1e-8
+                            and parity["C1_C1t_landmark_cols_max_rel_err"] < 1e-8)
+        del W, ones
+        # ---- the reference-signature API, from networkx graphs to host numpy arrays
+        if not args.no_api:
+            import munk_b200 as munk
+            import synth
+            c = synth.CONFIGS[args.config]
+            G1, G2, homs = synth.make_case(n1, n2, c[2], min(c[3], n1, n2), seeds=(1, 2))
+            del sink
+            times = []
+            for _ in range(2):
+                ta = time.time()
+                (C1a, _), (C2a, _), _, rts = munk.embed_networks(G1, G2, homs, k)
+                tb = time.time()
+                Sa = munk.scores(C1a, C2a)
+                times.append((time.time() - ta, tb - ta))
+            apar = parity_vs_checker(Sa, chk, inp["landmark_idxs"], "munk.scores(*munk.embed_networks(...))")
+            best = min(times)
+            api = {"seconds": best[0], "embed_networks_s": best[1], "scores_s": best[0] - best[1],
+                   "value": fl["total"] / best[0] / 1e12, "unit": UNIT, "runs_s": [round(t[0], 3) for t in times],
+                   "runtimes": rts, "S_max_rel_err": apar["S_max_rel_err"],
+                   "call": "munk.embed_networks(G1, G2, homologs, %d) + munk.scores(C1, C2hat): networkx graphs in, "
+                           "host numpy C1 / C2hat / S out (pageable memory)" % k}
+            del C1a, C2a, Sa, G1, G2
+        del chk
+
     # ---- max over ranks
     if world > 1:
         t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=tdev)
@@ -407,10 +608,10 @@ def run_gpu(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: source %d / target %d nodes, %d landmarks, lam 0.05, Barabasi-Albert m=10 "
-                                   "(seeds 1+2r/2+2r), one graph pair per GPU" % (args.config, n1, n2, k),
-                       "parallelism": "1 GPU" if world == 1 else "replicas: one independent graph pair per GPU, no collective",
+            "scaling": "strong" if world == 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, n1, n2, k),
+                       "parallelism": "1 GPU" if world == 1 else
+                                      "replicas: one independent graph pair per GPU (seeds 1+2r/2+2r), no collective",
                        "l2": "inputs larger than L2: %.1f GB of FP64 matrices per step vs 126 MB L2" % (
                            (n1 * n1 + n2 * n2 + 2 * n1 * n2) * 8 / 1e9),
                        "useful_tflop_per_step": fl["total"] / 1e12, "seconds_per_pipeline": ms_step * 1e-3},
@@ -436,11 +637,10 @@ def run_gpu(args):
             "phases": phases,
             "counted_tile_flops_per_step": counted_flops / args.steps,
         }
+        line["parity"] = parity
+        line["api_e2e"] = api
         if not args.no_cpu and world == 1:
-            info = cpu_info()
-            tf, secs, desc = cpu_sample(args.config, args.cpu_n1, args.cpu_n2)
-            line["cpu_baseline"] = {"value": tf, "unit": UNIT, "cores": info.get("threads"), "kind": "port",
-                                    "sample": desc, "host": info}
+            line["cpu_baseline"] = cpu_baseline_leg(args.config, max(200, n1 // 4), max(150, n2 // 4))
         else:
             line["cpu_baseline"] = None
         emit(line)
@@ -546,6 +746,43 @@ def run_gpu_dist(args, dev, rank, world, local):
         rank, trace["start"].elapsed_time(trace["compute"]),
         {kk: round(trace["start"].elapsed_time(e), 1) for kk, e in sink.done.items()}), file=sys.stderr, flush=True)
 
+    # ---- parity (outside the timed regions): every rank's score rows — of one more device step and
+    # of the host copies the e2e steps left in the ShardSink — against the CPU checker's S, which
+    # rank 0 computes (no GPU data) and broadcasts
+    parity = None
+    if not args.no_parity:
+        out = step(e1, e2)
+        rows_t = torch.as_tensor(np.asarray(out["rows"], dtype=np.int64), device=tdev)
+        S_ref = torch.empty((n1, n2), dtype=torch.float64, device=tdev)
+        meta = torch.zeros(3, dtype=torch.float64, device=tdev)
+        chk = None
+        if rank == 0:
+            chk = cpu_checker(n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"])
+            S_ref.copy_(torch.from_numpy(chk["S"]))
+            meta[0], meta[1] = float(np.abs(chk["S"]).max()), chk["seconds"]
+        dist.broadcast(S_ref, src=0)
+        dist.broadcast(meta, src=0)
+        errs = torch.zeros(3, dtype=torch.float64, device=tdev)
+        if len(out["rows"]):
+            mine = S_ref[rows_t]
+            errs[0] = (out["S"][:, :n2] - mine).abs().max()
+            errs[1] = (sink.S.to(tdev) - mine).abs().max()
+            errs[2] = float(len(out["rows"]))
+            del mine
+        emax = errs.clone(); dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+        esum = errs.clone(); dist.all_reduce(esum, op=dist.ReduceOp.SUM)
+        scale = float(meta[0])
+        parity = {"S_max_rel_err": float(emax[0]) / scale, "e2e_S_max_rel_err": float(emax[1]) / scale,
+                  "tolerance": 1e-8, "ok": bool(float(emax[0]) / scale <= 1e-8 and float(emax[1]) / scale <= 1e-8
+                                                and int(esum[2]) == n1),
+                  "rows_compared": int(esum[2]), "cells_compared": int(esum[2]) * n2,
+                  "what": "the row shards of S on all %d ranks (device result of one more step, and the pinned host "
+                          "copies of the e2e steps), max over ranks" % world,
+                  "checker": "oracle.scores_by_cholesky on rank 0: CPU LAPACK Cholesky route, no GPU data; pinned to "
+                             "the reference's S in tests/test_oracle.py; %.1f s on %d host threads" % (
+                                 float(meta[1]), host_cores())}
+        del out, S_ref, chk
+
     t = torch.tensor([ms, e2e_ms, float(h2d), float(d2h), float(launches)], dtype=torch.float64, device=tdev)
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
@@ -566,10 +803,9 @@ def run_gpu_dist(args, dev, rank, world, local):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: source %d / target %d nodes, %d landmarks, lam 0.05, Barabasi-Albert m=10 "
-                                   "(seeds 1/2), ONE graph pair sharded over %d GPUs" % (args.config, n1, n2, k, world),
-                       "parallelism": "1 x %d block-column-cyclic Cholesky (NCCL panel broadcasts), per-rank column "
-                                      "solves, row-sharded score product" % world,
+            "config": {"workload": workload_name(args.config, n1, n2, k),
+                       "parallelism": "ONE graph pair sharded over %d GPUs: 1 x %d block-column-cyclic Cholesky (NCCL "
+                                      "panel broadcasts), per-rank column solves, row-sharded score product" % (world, world),
                        "l2": "inputs larger than L2: %.1f GB of FP64 matrices per step vs 126 MB L2" % (
                            (n1 * n1 + n2 * n2 + 2 * n1 * n2) * 8 / 1e9),
                        "useful_tflop_per_step": fl["total"] / 1e12, "seconds_per_pipeline": ms_step * 1e-3},
@@ -584,6 +820,7 @@ def run_gpu_dist(args, dev, rank, world, local):
                                    "(staircase k-range, %.2f TFLOP)" % (rows0, score_flops0 / 1e12),
                          "peak_source": "measured in this run on rank 0: FP64 DMMA issue-rate microbenchmark"},
             "phases": {kk: {"ms": vv} for kk, vv in med.items()},
+            "parity": parity,
             "cpu_baseline": None,
         }
         emit(line)
@@ -599,14 +836,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="C3")
     ap.add_argument("--impl", default="munk_b200", choices=["munk_b200", "reference"])
-    ap.add_argument("--cpu-n1", dest="cpu_n1", type=int, default=5000)
-    ap.add_argument("--cpu-n2", dest="cpu_n2", type=int, default=4000)
-    ap.add_argument("--cpu-max-steps", dest="cpu_max_steps", type=int, default=5)
-    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--ref-n1", dest="ref_n1", type=int, default=0,
+                    help="reference arm: time this same-shape sample instead of the full configuration")
+    ap.add_argument("--ref-n2", dest="ref_n2", type=int, default=0)
+    ap.add_argument("--no-cache", dest="no_cache", action="store_true")
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the CPU parity check")
+    ap.add_argument("--no-api", dest="no_api", action="store_true", help="skip the api_e2e measurement")
     args = ap.parse_args()
     if args.impl == "reference":
+        force_host_threads()
         run_reference(args)
     else:
+        if int(os.environ.get("RANK", "0")) == 0:
+            force_host_threads()          # rank 0 runs the CPU parity checker after the timed regions
         run_gpu(args)
 
 

@@ -26,7 +26,7 @@ sys.modules["sklearn.externals.joblib"] = joblib
 sys.path.insert(0, "/root/reference/munk")
 import munk as ref  # noqa: E402  (the reference package)
 
-from munk_b200 import synthetic  # noqa: E402
+import synth as synthetic  # noqa: E402
 from oracle import munk_oracle as oracle  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")

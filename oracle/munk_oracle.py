@@ -185,6 +185,56 @@ def effect_size(observed, control):
 
 
 # --------------------------------------------------------------------------------------
+# full-size checker: the same scores without inv / eigh / pinv (seconds instead of minutes)
+# --------------------------------------------------------------------------------------
+def spd_matrix(n, edges, lam):
+    """np.eye(n) + lam * L (munk.py:83) built in one float64 buffer: the diagonal is
+    fl(1 + fl(lam * deg)), off-diagonals fl(lam * -1) — the same roundings as reglap_matrix()
+    (checked bit for bit in tests/test_oracle.py) without its int64 and float temporaries, so a
+    20 000-node matrix costs 3.2 GB instead of 13."""
+    A = np.zeros((n, n), dtype=np.float64)
+    u, v = edges[:, 0], edges[:, 1]
+    A[u, v] = lam * -1.0
+    A[v, u] = lam * -1.0
+    deg = np.bincount(np.concatenate([u, v]), minlength=n).astype(np.float64)
+    A[np.arange(n), np.arange(n)] = 1.0 + lam * deg
+    return A
+
+
+def scores_by_cholesky(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.05):
+    """The score matrix of embed_networks + scores (munk.py:114-176, compute_embeddings.py:81)
+    computed on the CPU WITHOUT the reference's inv / eigh / pinv calls, for checks at sizes where
+    those take minutes (BASELINE configs 2, 3, 5).  For distinct source landmarks Ls the rows
+    M = C1[Ls,:] are independent (M M^T = D1[Ls,Ls] is a principal block of an SPD matrix), so
+    pinv(M) = M^T (M M^T)^-1 exactly and
+
+        S = C1 pinv(M) D2[Lt,:] = D1[:,Ls] D1[Ls,Ls]^-1 D2[Lt,:]         
+
+    which needs only k columns of each kernel: two LAPACK Cholesky factorisations (scipy
+    cho_factor) and 2k right-hand sides.  Independent of every GPU result.  Pinned against the
+    reference's own S on the golden cases in tests/test_oracle.py (<= 1e-12 of max|S|).
+    Returns dict(S, D1_cols = D1[:,Ls] (n1 x k), D2_rows = D2[Lt,:] (k x n2))."""
+    ls = np.array([a for a, _ in landmark_idxs], dtype=np.int64)
+    lt = np.array([b for _, b in landmark_idxs], dtype=np.int64)
+    assert len(set(ls.tolist())) == len(ls), "scores_by_cholesky needs distinct source landmarks"
+    k = len(ls)
+
+    def kernel_columns(n, edges, lam, cols):
+        A = spd_matrix(n, np.asarray(edges).reshape(-1, 2), lam)
+        c = scipy.linalg.cho_factor(A, lower=True, overwrite_a=True, check_finite=False)
+        E = np.zeros((n, len(cols)), order="F")
+        E[cols, np.arange(len(cols))] = 1.0
+        return scipy.linalg.cho_solve(c, E, overwrite_b=True, check_finite=False)
+
+    X = kernel_columns(n1, edges1, src_lam, ls)                   # D1[:, Ls]
+    B = kernel_columns(n2, edges2, tgt_lam, lt).T                 # D2[Lt, :] (D2 symmetric)
+    G = X[ls, :]                                                  # D1[Ls, Ls]
+    G = 0.5 * (G + G.T)
+    Z = scipy.linalg.cho_solve(scipy.linalg.cho_factor(G, lower=True), np.ascontiguousarray(B))
+    return dict(S=X @ Z, D1_cols=X, D2_rows=np.ascontiguousarray(B))
+
+
+# --------------------------------------------------------------------------------------
 # parity metrics used by the tests
 # --------------------------------------------------------------------------------------
 def rel_max_err(x, ref):

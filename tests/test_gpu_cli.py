@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_cli_outputs_match_reference_schema_and_oracle(tmp_path):
-    from munk_b200 import synthetic
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(400, 350, 3, 70, seeds=(71, 72), padded=False)
     # a pendant chain that the 2-core must remove, a second component, a self loop, duplicate lines
     G1.add_edges_from([("s0", "tail1"), ("tail1", "tail2"), ("iso1", "iso2"), ("iso2", "iso3"), ("iso3", "iso1")])

@@ -141,7 +141,8 @@ def test_target_rows_from_factor_equals_inverse_rows(dev):
 def test_permutation_unit_and_experiment(dev):
     """difference_in_means (permtest.py:68-80) on host arrays vs the oracle, and the sharded
     experiment in 'indices' mode vs the oracle run permutation by permutation."""
-    from munk_b200 import permtest, synthetic
+    from munk_b200 import permtest
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(260, 220, 4, 60, seeds=(31, 32))
     k = 15
     ref = oracle.embed_networks(G1, G2, homs, k)
@@ -167,7 +168,8 @@ def test_streamed_outputs_equal_direct_outputs(dev):
     """HostSink path (results copied out on a second stream while later stages run, scores in
     row blocks) gives the same arrays as the plain serial device path (to rounding: the row-block
     launches pick different split-K factors, i.e. a different summation order)."""
-    from munk_b200 import pipeline, synthetic
+    from munk_b200 import pipeline
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(1500, 900, 4, 80, seeds=(51, 52))
     res = pipeline.embed_and_score(G1, G2, homs, 30)
     inp = pipeline.graph_inputs(G1, G2, homs, 30)
@@ -204,7 +206,8 @@ def test_download_upper_moves_exactly_the_triangle(dev, n, row_block, pinned):
 def test_distributed_driver_single_rank_matches_oracle(dev):
     """munk_b200.dist with world = 1 (same code path as N ranks, minus the broadcasts): panel
     driver, staircase solve for the W columns + landmark columns, staircase score product, means."""
-    from munk_b200 import dist as mdist, pipeline, synthetic
+    from munk_b200 import dist as mdist, pipeline
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(1300, 700, 4, 90, seeds=(41, 42))
     homs = homs[:7] + [(homs[3][0], homs[50][1])] + homs[7:]            # one repeated source landmark
     k = 40
@@ -268,7 +271,8 @@ def test_rank_deficient_landmark_rows_follow_pinv(dev):
 def test_rank_k_statistic_matches_dense_path(dev):
     """Opt-in fast path (no S formed) vs the dense unit, incl. a repeated source landmark and
     homolog cells inside landmark rows/columns."""
-    from munk_b200 import permtest, pipeline, synthetic
+    from munk_b200 import permtest, pipeline
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(900, 700, 4, 120, seeds=(61, 62))
     homs = homs[:5] + [(homs[2][0], homs[40][1]), (homs[50][0], homs[3][1])] + homs[5:]
     k = 25
@@ -286,7 +290,8 @@ def test_random_network_generator(dev):
     """gen_random_network_data (gen_random_network.py:78-84): same nodes and degrees as the seed
     graph, D and C consistent with the oracle on the generated graph."""
     import networkx as nx
-    from munk_b200 import permtest, synthetic
+    from munk_b200 import permtest
+    import synth as synthetic
     seed_G = oracle.simple_two_core(synthetic.ba_graph(150, 4, 3, "g"))
     data, tries = permtest.gen_random_network_data(seed_G, n_tries=50, rng=np.random.default_rng(5))
     G = data["G"]

@@ -32,7 +32,7 @@ def test_cli_under_torchrun_matches_single_gpu_cli(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    from munk_b200 import synthetic
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(1300, 900, 4, 90, seeds=(5, 6))
     synthetic.write_edgelist(G1, tmp_path / "src.txt")
     synthetic.write_edgelist(G2, tmp_path / "tgt.txt")

@@ -105,7 +105,7 @@ def test_assembly_bit_exact(m):
 
 @pytest.fixture(scope="module")
 def c1_case():
-    from munk_b200 import synthetic
+    import synth as synthetic
     n1, n2, mm, H, k = synthetic.CONFIGS["C1"]
     G1, G2, homs = synthetic.make_case(n1, n2, mm, H)
     G1, G2 = oracle.simple_two_core(G1), oracle.simple_two_core(G2)
@@ -159,7 +159,7 @@ def test_c1_device_pipeline_and_means(m, c1_case):
 def test_one_to_many_homologs_match_pinv(m):
     """A source landmark listed twice makes C1[Ls,:] rank deficient: np.linalg.pinv returns the
     rank-(k-1) least-squares answer and so must we."""
-    from munk_b200 import synthetic
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(300, 260, 4, 60, seeds=(7, 8))
     homs = homs[:9] + [(homs[2][0], homs[30][1]), (homs[2][0], homs[31][1])] + homs[9:]
     k = 20
@@ -179,7 +179,7 @@ def test_ragged_sizes(m, n1, n2, mm, H, k):
         G2 = nx.relabel_nodes(nx.cycle_graph(4), {i: "t%d" % i for i in range(4)})
         homs = [("s0", "t1"), ("s2", "t0"), ("s1", "t3")]
     else:
-        from munk_b200 import synthetic
+        import synth as synthetic
         G1, G2, homs = synthetic.make_case(n1, n2, mm, H, seeds=(n1, n2), padded=False)
     ref = oracle.embed_networks(G1, G2, homs, k)
     (C1, s_nodes), (C2, _), l_idx, h_idx = m.embed_networks(G1, G2, homs, k, return_idxs=True)
@@ -216,7 +216,8 @@ def test_c3_full_size_properties(m):
     D 1 = 1, S[Ls,:] = D2[Lt,:] (interpolation), S = D1[:,Ls] D1[Ls,Ls]^-1 D2[Lt,:] on sampled
     columns, exact integer outputs, and an fp64 residual check of the factor on sampled rows."""
     import torch
-    from munk_b200 import pipeline, synthetic
+    from munk_b200 import pipeline
+    import synth as synthetic
     n1, n2, mm, H, k = synthetic.CONFIGS["C3"]
     G1, G2, homs = synthetic.make_case(n1, n2, mm, H)
     inp = pipeline.graph_inputs(G1, G2, homs, k)

@@ -60,7 +60,8 @@ def test_edge_index_arrays_rules():
 
 
 def test_file_formats_roundtrip(tmp_path):
-    from munk_b200 import synthetic, util
+    from munk_b200 import util
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(60, 50, 3, 20, seeds=(5, 6))
     synthetic.write_edgelist(G1, tmp_path / "s.txt", extras=True)
     synthetic.write_homologs(homs, tmp_path / "h.tsv")

@@ -78,7 +78,8 @@ def test_ingest_refuses_weights_and_bad_data(tmp_path):
 
 
 def test_homolog_filter_and_index_inputs_match_graph_path(tmp_path):
-    from munk_b200 import pipeline, synthetic
+    from munk_b200 import pipeline
+    import synth as synthetic
     G1, G2, homs = synthetic.make_case(120, 90, 3, 30, seeds=(5, 6), padded=False)
     synthetic.write_edgelist(G1, tmp_path / "s.txt", extras=True)
     synthetic.write_edgelist(G2, tmp_path / "t.txt", extras=True)

@@ -99,3 +99,51 @@ def test_permutation_statistics():
     p, n_sig, n = oracle.one_tail_pval(0.25, d)
     assert (p, n_sig, n) == (0.5, 2.0, 4.0)
     assert abs(oracle.effect_size(0.25, d) - (0.25 - d.mean()) / d.std()) < 1e-15
+
+
+def test_cholesky_checker_matches_reference_scores(golden):
+    """oracle.scores_by_cholesky (the full-size checker used at BASELINE configs 2/3/5 and inside
+    bench.py's `parity` object) against the reference's own S."""
+    if golden["name"] == "dup_source_landmark":
+        return                                         # the checker requires distinct source landmarks
+    n1, n2 = len(golden["source_nodes"]), len(golden["target_nodes"])
+    e1, e2 = golden["source_edges"].astype(np.int64), golden["target_edges"].astype(np.int64)
+    assert np.array_equal(oracle.spd_matrix(n1, e1, float(golden["lam"])),
+                          oracle.reglap_matrix(n1, e1, float(golden["lam"])))
+    l = golden["landmark_idxs"]
+    out = oracle.scores_by_cholesky(n1, e1, n2, e2, pairs(l))
+    assert oracle.rel_max_err(out["S"], golden["S"]) < 1e-12
+    assert oracle.rel_max_err(out["D1_cols"], golden["D1"][:, l[:, 0]]) < 1e-12
+    assert oracle.rel_max_err(out["D2_rows"], golden["D2"][l[:, 1], :]) < 1e-12
+
+
+def test_installed_reference_agrees_with_oracle():
+    """oracle/_ref (the unmodified reference, pip-installed by oracle/build_ref.py; what
+    `bench.py --impl reference` times) gives bit-for-bit the oracle's numbers."""
+    import subprocess
+    import sys
+    import os
+    import pytest
+    from oracle import build_ref
+    if not build_ref.installed():
+        pytest.skip("oracle/_ref not installed (run python oracle/build_ref.py where /root/reference exists)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # a fresh interpreter: this process already has the drop-in `munk` alias importable
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from oracle import build_ref, munk_oracle as oracle\n"
+        "import synth\n"
+        "ref = build_ref.load()\n"
+        "assert 'munk_b200' not in sys.modules\n"
+        "G1, G2, homs = synth.make_case(90, 70, 3, 25, seeds=(3, 4))\n"
+        "(C1, sn), (C2, tn), lh, rt = ref.embed_networks(G1, G2, homs, 10)\n"
+        "S = np.dot(C1, C2.T)\n"
+        "o = oracle.embed_networks(G1, G2, homs, 10)\n"
+        "assert sn == o['source_nodes'] and tn == o['target_nodes'] and lh == o['landmark_homs']\n"
+        "assert np.array_equal(C1, o['C1']) and np.array_equal(C2, o['C2'])\n"
+        "assert np.array_equal(S, oracle.scores(o['C1'], o['C2']))\n"
+        "assert sorted(rt) == ['embed_runtime', 'source_regularized_laplacian_runtime',"
+        " 'source_rkhs_factorization_runtime', 'target_regularized_laplacian_runtime']\n"
+        "print('ok')\n" % root)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr

@@ -13,7 +13,7 @@ import time
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
-from munk_b200 import synthetic  # noqa: E402
+import synth as synthetic  # noqa: E402
 
 
 def main():
