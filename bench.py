@@ -423,7 +423,8 @@ def run_gpu(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     phase_ms = {}
     from munk_b200.device import side_device
-    dev2, side = side_device(dev)
+    dev2, side, tgt_stream = side_device(dev)
+    verdicts = []
 
     def step(edges1, edges2, uniq_idx, tgt_idx, record=False):
         marks = []
@@ -432,11 +433,13 @@ def run_gpu(args):
             if record:
                 e = ev(); e.record(); marks.append((name, e))
         mark("start")
-        # Source chain first, on the high-priority stream; the independent target chain is
-        # enqueued behind it on the current stream (second workspace) and fills the SMs the
-        # source's latency-bound panel steps leave idle.
+        # Source chain on the high-priority stream, the independent target chain on a second
+        # stream with its own workspace: it fills the SMs the source's latency-bound block-column
+        # chain leaves idle.  Both factorisations replay cached CUDA graphs, so the host enqueues
+        # each chain in well under a millisecond.
         main = torch.cuda.current_stream()
         side.wait_stream(main)
+        tgt_stream.wait_stream(main)
         with torch.cuda.stream(side):
             h0 = ev(); h0.record()
             dev.assemble(n1, edges1[0], edges1[1], 0.05, out=A1)
@@ -445,15 +448,20 @@ def run_gpu(args):
             h2 = ev(); h2.record()
             dev.trtri(A1, n1, linv1)
             h3 = ev(); h3.record()
-        s0 = ev(); s0.record()
-        dev2.assemble(n2, edges2[0], edges2[1], 0.05, out=A2)
-        dev2.potrf(A2, n2, linv=linv2, check_info=False)
-        s1 = ev(); s1.record()
-        B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, tgt_idx)
-        s2 = ev(); s2.record()
-        main.wait_stream(side); mark("factor_chains")
+        with torch.cuda.stream(tgt_stream):
+            s0 = ev(); s0.record()
+            dev2.assemble(n2, edges2[0], edges2[1], 0.05, out=A2)
+            dev2.potrf(A2, n2, linv=linv2, check_info=False)
+            s1 = ev(); s1.record()
+            B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, tgt_idx)
+            s2 = ev(); s2.record()
+        main.wait_stream(side)
+        main.wait_stream(tgt_stream)
+        B.record_stream(main)
+        mark("factor_chains")
         Q1 = dev.gather_cols_lower(A1, n1, uniq_idx)
-        P = dev.project(Q1, n1, B, n2, (gptr, members)); mark("embed")
+        P, verdict = dev.project(Q1, n1, B, n2, (gptr, members), defer=True); mark("embed")
+        verdicts.append(verdict.bad)
         dev.score(A1, n1, P, n2, out=S_buf); mark("score")
         if record:
             torch.cuda.current_stream().synchronize()
@@ -491,6 +499,7 @@ def run_gpu(args):
     launches, counted_flops = launches + l2_, counted_flops + f2_
     clocks = sampler.stop()
     assert dev.potrf_info() == 0 and dev2.potrf_info() == 0
+    assert not bool(torch.stack(verdicts).any()), "the fast landmark solve was flagged unsafe"
 
     # ---- timed: e2e (host buffers in, pinned host results out, every step)
     h_e1 = [torch.from_numpy(x).pin_memory() for x in inp["edges1"]]
@@ -506,6 +515,7 @@ def run_gpu(args):
                                     keep_target_factor=False, sink=sink)
         emb.scores_streamed(sink)
         sink.wait()
+        emb.finalize()                      # factorisation flags + projection verdict (16 bytes D2H)
         torch.cuda.current_stream().synchronize()
 
     e2e_step()

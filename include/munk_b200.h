@@ -27,6 +27,8 @@ extern "C" {
 #endif
 
 typedef struct munk_workspace munk_workspace_t; /* per-stream scratch + statistics */
+typedef struct munk_comm munk_comm_t;           /* one NCCL communicator (multi-GPU entry points) */
+typedef struct munk_dist munk_dist_t;           /* one matrix being factored over the ranks of a communicator */
 
 /* Operand storage for munk_dgemm: the contraction index k contiguous, or the free index. */
 #define MUNK_OP_KC 0 /* X[i*ld + k] */
@@ -60,6 +62,21 @@ size_t munk_linv_bytes(int n);
  */
 int munk_assemble_reglap(munk_workspace_t* ws, int n, int nnz, const int* u, const int* v,
                          double lam, double* A, long ld, void* stream);
+/* An edge with an endpoint outside [0, n) is skipped (never written) and remembered:
+ * munk_assemble_info synchronises `stream` and returns 1 + the index of the first such edge in
+ * *bad_edge_host (0 = every edge was in range); the device flag is cleared. */
+int munk_assemble_info(munk_workspace_t* ws, int* bad_edge_host, void* stream);
+
+/*
+ * The same from explicit Laplacian entries, for graphs whose Laplacian is not 0/-1/degree
+ * (edge weights, parallel edges of a MultiGraph - nx.laplacian_matrix sums them,
+ * munk/munk/munk.py:82): lval[e] = L[u[e]][v[e]] (each unordered pair once), ldiag[i] = L[i][i],
+ * both float64 exactly as networkx produced them.  A[u][v] = A[v][u] = fl(lam * lval),
+ * A[i][i] = fl(1 + fl(lam * ldiag[i])): bit-exact with np.eye(n) + lam * L.
+ */
+int munk_assemble_reglap_entries(munk_workspace_t* ws, int n, int nnz, const int* u, const int* v,
+                                 const double* lval, const double* ldiag, double lam, double* A,
+                                 long ld, void* stream);
 
 /*
  * In-place lower Cholesky A = L L^T (row-major; lower triangle read and written; the 128x128
@@ -197,18 +214,76 @@ int munk_pair_dots(int npairs, const int* r, const int* c, int k, const double* 
                    const double* Z, long ldz, double* out, void* stream);
 
 /*
- * Z (k x n) = pinv(G) B for a symmetric positive semi-definite k x k matrix G (overwritten):
- * one-sided Jacobi eigen-decomposition on the device, eigenvalues <= max(rcond^2, 4 k eps) *
- * lambda_max truncated; *rank_host receives the retained rank.  Synchronises `stream`.
- * `work` holds munk_sym_pinv_work_bytes(k, n) bytes.  Rank-revealing fallback for
- * np.linalg.pinv(source_C[source_idxs,:]) (munk/munk/munk.py:109) when the landmark Gram matrix
- * is not safely positive definite; G = M M^T squares the singular values of M, so singular
- * values of M below ~sqrt(4 k eps) sigma_max count as zero (numpy's cut is 1e-15 sigma_max).
+ * Rank-revealing pseudo-inverse solve on the landmark rows themselves, numpy semantics
+ * (np.linalg.pinv(source_C[source_idxs,:]) at munk/munk/munk.py:109: singular values
+ * <= rcond * sigma_max dropped, rcond = 1e-15).  R (k x m, row-major) holds the landmark rows M on
+ * entry; one-sided Jacobi rotations from the left make its rows orthogonal, R <- J M.  On return
+ *     Z (k x n) = diag(1 / sigma_i^2 if sigma_i > rcond * sigma_max else 0) (J B),
+ * so that pinv(M) B = R^T Z (one munk_dgemm with R as an MC-layout operand).  *rank_host receives
+ * the retained rank, sigma_host (k doubles, may be NULL) the singular values.  Synchronises
+ * `stream` once per sweep.  `work` holds munk_pinv_rows_work_bytes(k) bytes.  This is the robust
+ * path; the hot path solves with the Cholesky factor of M M^T when a device-side condition bound
+ * allows it (munk_b200/device.py).
  */
-int munk_sym_pinv_solve(munk_workspace_t* ws, int k, double* G, long ldg, int n, const double* B,
-                        long ldb, double* Z, long ldz, double* work, double rcond, int* rank_host,
-                        void* stream);
-size_t munk_sym_pinv_work_bytes(int k, int n);
+int munk_pinv_rows_solve(munk_workspace_t* ws, int k, int m, double* R, long ldr, int n,
+                         const double* B, long ldb, double* Z, long ldz, double* work, double rcond,
+                         int* rank_host, double* sigma_host, void* stream);
+size_t munk_pinv_rows_work_bytes(int k);
+
+/*
+ * ---- multi-GPU (one process per GPU, NCCL over NVLink; munk_b200/csrc/dist.cu) -------------------
+ * Replaces np.linalg.inv (munk/munk/munk.py:83) and the eigh factor (munk.py:87-88) for a matrix
+ * whose block columns (width munk_dist_block() = 512) are dealt to the ranks in serpentine rounds
+ * (rank of block j: r = j mod P in even rounds, P-1-r in odd rounds).  NCCL is taken from the
+ * process at run time (dlopen of libnccl.so.2); status codes >= 4000 are 4000 + ncclResult_t.
+ *
+ * Communicator: rank 0 calls munk_comm_unique_id and ships the 128 bytes to the other ranks by
+ * any means (torch.distributed in munk_b200/dist.py); every rank then calls munk_comm_create.
+ * world = 1 needs no id and no NCCL.
+ */
+int munk_dist_block(void);
+int munk_comm_unique_id(void* id128);
+int munk_comm_create(int device, int rank, int world, const void* id128, munk_comm_t** comm);
+int munk_comm_destroy(munk_comm_t* comm);
+
+/*
+ * Panel-major factor storage: block column c is one contiguous buffer [leaf inverses | rows
+ * s_c..n, leading dimension round_up(w_c, 16)], the owner's working storage and the other ranks'
+ * broadcast buffer at once.  `storage` holds munk_dist_storage_elems(n) doubles (about n^2/2),
+ * 16-byte aligned, owned by the caller, and must outlive the handle.  comm = NULL: one rank.
+ */
+size_t munk_dist_storage_elems(int n);
+int munk_dist_create(munk_workspace_t* ws, munk_comm_t* comm, int n, double* storage, munk_dist_t** dist);
+int munk_dist_destroy(munk_dist_t* dist);
+int munk_dist_blocks(munk_dist_t* dist);
+
+/* I + lam L into the block columns this rank owns (lval/ldiag NULL: unweighted, as
+ * munk_assemble_reglap; otherwise as munk_assemble_reglap_entries).  Bit-exact with numpy. */
+int munk_dist_assemble(munk_dist_t* dist, int nnz, const int* u, const int* v, const double* lval,
+                       const double* ldiag, double lam, void* stream);
+
+/* Right-hand side of the fused forward substitution: X (n x ncols, row-major, ldx) <- L^-1 X,
+ * applied panel by panel while the factorisation runs.  `stair` (device, one int per 128 columns,
+ * or NULL): first non-zero row of each column tile (identity columns: only the non-zero part of
+ * every column is computed).  X = NULL: factorisation only. */
+int munk_dist_set_rhs(munk_dist_t* dist, double* X, long ldx, int ncols, const int* stair);
+
+/* The factorisation, one block column per step so that a caller can interleave several
+ * matrices from one host thread (every rank must make the same sequence of calls): begin forks
+ * the library's streams from `stream`, step enqueues the next block column (*remaining = block
+ * columns still to go), end enqueues whatever is left and joins everything back into `stream`.
+ * The non-SPD flag is the workspace's (munk_potrf_info / munk_potrf_info_async). */
+int munk_dist_potrf_begin(munk_dist_t* dist, void* stream);
+int munk_dist_potrf_step(munk_dist_t* dist, int* remaining);
+int munk_dist_potrf_end(munk_dist_t* dist);
+
+/* X (n x ncols, in place) <- L^-T X with the finished factor (every rank holds all of it):
+ * with munk_dist_set_rhs this gives A^-1 X, i.e. target_D[:, target_idxs] (munk/munk/munk.py:110). */
+int munk_dist_solve_backward(munk_dist_t* dist, double* X, long ldx, int ncols, void* stream);
+
+/* L (n x ld, row-major, lower triangle incl. zeros above the diagonal inside the diagonal blocks)
+ * <- the panel-major factor (tests, tools). */
+int munk_dist_unpack(munk_dist_t* dist, double* L, long ld, void* stream);
 
 /* Micro-benchmarks used by bench.py / tools to measure the FP64 ceilings of the box.
  * Each runs on `device`, blocks, and returns TFLOP/s in *tflops. */

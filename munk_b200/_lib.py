@@ -23,6 +23,9 @@ SIGNATURES = {
     "munk_linv_bytes": (c_size_t, [c_int]),
     "munk_assemble_reglap": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_double,
                                      c_void_p, c_long, c_void_p]),
+    "munk_assemble_info": (c_int, [c_void_p, _P(c_int), c_void_p]),
+    "munk_assemble_reglap_entries": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_double, c_void_p, c_long, c_void_p]),
     "munk_potrf": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p]),
     "munk_potrf_info": (c_int, [c_void_p, _P(c_int), c_void_p]),
     "munk_potrf_info_async": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -53,9 +56,24 @@ SIGNATURES = {
                                            c_void_p]),
     "munk_pair_dots": (c_int, [c_int, c_void_p, c_void_p, c_int, c_void_p, c_long, c_void_p, c_long,
                                c_void_p, c_void_p]),
-    "munk_sym_pinv_solve": (c_int, [c_void_p, c_int, c_void_p, c_long, c_int, c_void_p, c_long, c_void_p,
-                                    c_long, c_void_p, c_double, _P(c_int), c_void_p]),
-    "munk_sym_pinv_work_bytes": (c_size_t, [c_int, c_int]),
+    "munk_pinv_rows_solve": (c_int, [c_void_p, c_int, c_int, c_void_p, c_long, c_int, c_void_p, c_long,
+                                     c_void_p, c_long, c_void_p, c_double, _P(c_int), c_void_p, c_void_p]),
+    "munk_pinv_rows_work_bytes": (c_size_t, [c_int]),
+    "munk_dist_block": (c_int, []),
+    "munk_comm_unique_id": (c_int, [c_void_p]),
+    "munk_comm_create": (c_int, [c_int, c_int, c_int, c_void_p, _P(c_void_p)]),
+    "munk_comm_destroy": (c_int, [c_void_p]),
+    "munk_dist_storage_elems": (c_size_t, [c_int]),
+    "munk_dist_create": (c_int, [c_void_p, c_void_p, c_int, c_void_p, _P(c_void_p)]),
+    "munk_dist_destroy": (c_int, [c_void_p]),
+    "munk_dist_blocks": (c_int, [c_void_p]),
+    "munk_dist_assemble": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
+    "munk_dist_set_rhs": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
+    "munk_dist_potrf_begin": (c_int, [c_void_p, c_void_p]),
+    "munk_dist_potrf_step": (c_int, [c_void_p, _P(c_int)]),
+    "munk_dist_potrf_end": (c_int, [c_void_p]),
+    "munk_dist_solve_backward": (c_int, [c_void_p, c_void_p, c_long, c_int, c_void_p]),
+    "munk_dist_unpack": (c_int, [c_void_p, c_void_p, c_long, c_void_p]),
     "munk_microbench_dmma": (c_int, [c_int, c_int, _P(c_double)]),
     "munk_microbench_dfma": (c_int, [c_int, c_int, _P(c_double)]),
 }

@@ -78,16 +78,45 @@ int munk_assemble_reglap(munk_workspace_t* ws, int n, int nnz, const int* u, con
   if (!ws) return -1;
   if (n < 0) return -2;
   if (nnz < 0) return -3;
+  if (nnz > 0 && (!u || !v)) return -4;
   if (ld < n) return -8;
+  DeviceGuard guard(ws->device);
   // degree scratch: reuse the split-K buffer (never live at the same time on one stream)
   MUNK_TRY(ws->ensure_splitk(0, std::max(SPLITK_RESERVE, (size_t)(n + 2) * sizeof(int))));
-  MUNK_TRY(assemble_reglap(n, nnz, u, v, lam, A, ld, (int*)ws->splitk[0], S(stream)));
+  MUNK_TRY(assemble_reglap(n, nnz, u, v, nullptr, nullptr, lam, A, ld, (int*)ws->splitk[0], ws->info + 1,
+                           S(stream)));
   ws->launches += (nnz > 0) ? 3 : 1;
+  return MUNK_OK;
+}
+
+int munk_assemble_reglap_entries(munk_workspace_t* ws, int n, int nnz, const int* u, const int* v,
+                                 const double* lval, const double* ldiag, double lam, double* A,
+                                 long ld, void* stream) {
+  if (!ws) return -1;
+  if (n < 0) return -2;
+  if (nnz < 0) return -3;
+  if (nnz > 0 && (!u || !v || !lval)) return -4;
+  if (n > 0 && !ldiag) return -7;
+  if (ld < n) return -10;
+  DeviceGuard guard(ws->device);
+  MUNK_TRY(assemble_reglap(n, nnz, u, v, lval, ldiag, lam, A, ld, nullptr, ws->info + 1, S(stream)));
+  ws->launches += (nnz > 0) ? 2 : 1;
+  return MUNK_OK;
+}
+
+int munk_assemble_info(munk_workspace_t* ws, int* bad_edge_host, void* stream) {
+  if (!ws || !bad_edge_host) return -1;
+  DeviceGuard guard(ws->device);
+  MUNK_CUDA_TRY(cudaMemcpyAsync(ws->info_host + 1, ws->info + 1, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+  MUNK_CUDA_TRY(cudaMemsetAsync(ws->info + 1, 0, sizeof(int), S(stream)));
+  MUNK_CUDA_TRY(cudaStreamSynchronize(S(stream)));
+  *bad_edge_host = ws->info_host[1];
   return MUNK_OK;
 }
 
 int munk_potrf(munk_workspace_t* ws, int n, double* A, long ld, double* linv, void* stream) {
   if (!ws) return -1;
+  DeviceGuard guard(ws->device);
   if (n < 0) return -2;
   if (ld < n || (ld & 1)) return -4;
   if (!A || !linv) return -3;
@@ -96,6 +125,7 @@ int munk_potrf(munk_workspace_t* ws, int n, double* A, long ld, double* linv, vo
 
 int munk_potrf_info(munk_workspace_t* ws, int* info_host, void* stream) {
   if (!ws || !info_host) return -1;
+  DeviceGuard guard(ws->device);
   MUNK_CUDA_TRY(cudaMemcpyAsync(ws->info_host, ws->info, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
   MUNK_CUDA_TRY(cudaMemsetAsync(ws->info, 0, sizeof(int), S(stream)));
   MUNK_CUDA_TRY(cudaStreamSynchronize(S(stream)));
@@ -105,6 +135,7 @@ int munk_potrf_info(munk_workspace_t* ws, int* info_host, void* stream) {
 
 int munk_potrf_info_async(munk_workspace_t* ws, int* info_dev, void* stream) {
   if (!ws || !info_dev) return -1;
+  DeviceGuard guard(ws->device);
   MUNK_CUDA_TRY(cudaMemcpyAsync(info_dev, ws->info, sizeof(int), cudaMemcpyDeviceToDevice, S(stream)));
   MUNK_CUDA_TRY(cudaMemsetAsync(ws->info, 0, sizeof(int), S(stream)));
   return MUNK_OK;
@@ -112,6 +143,7 @@ int munk_potrf_info_async(munk_workspace_t* ws, int* info_dev, void* stream) {
 
 int munk_trtri(munk_workspace_t* ws, int n, double* L, long ld, double* linv, void* stream) {
   if (!ws) return -1;
+  DeviceGuard guard(ws->device);
   if (n < 0) return -2;
   if (ld < n || (ld & 1)) return -4;
   if (!L || !linv) return -3;
@@ -121,6 +153,7 @@ int munk_trtri(munk_workspace_t* ws, int n, double* L, long ld, double* linv, vo
 int munk_trsm_left(munk_workspace_t* ws, int n, const double* L, long ld, const double* linv,
                    int transposed, int nrhs, double* B, long ldb, const int* stair, void* stream) {
   if (!ws) return -1;
+  DeviceGuard guard(ws->device);
   if (n < 0) return -2;
   if (ld < n || (ld & 1)) return -4;
   if (nrhs < 0) return -7;
@@ -131,6 +164,7 @@ int munk_trsm_left(munk_workspace_t* ws, int n, const double* L, long ld, const 
 int munk_trsm_right(munk_workspace_t* ws, int m, double* B, long ldb, const double* L, long ldl,
                     int s, const double* linv, void* stream) {
   if (!ws) return -1;
+  DeviceGuard guard(ws->device);
   if (m < 0 || s < 0) return -2;
   if (ldb < s || (ldb & 1) || ldl < s || (ldl & 1)) return -4;
   return trsm_right(ws, m, B, ldb, L, ldl, s, linv, S(stream));
@@ -141,6 +175,7 @@ int munk_dgemm_stair(munk_workspace_t* ws, int a_layout, int b_layout, int M, in
                      double* C, long ldc, int flags, const int* stair_m, const int* stair_n,
                      int row0, int k0, void* stream) {
   if (!ws) return -1;
+  DeviceGuard guard(ws->device);
   if ((a_layout | b_layout) & ~1) return -2;
   if (M < 0 || N < 0 || K < 0) return -4;
   GemmDesc g{};
@@ -161,6 +196,7 @@ int munk_transpose(int rows, int cols, const double* in, long ldi, double* out, 
 int munk_gram_lower(munk_workspace_t* ws, int n, const double* W, long ldw, double* D, long ldd,
                     void* stream) {
   if (!ws) return -1;
+  DeviceGuard guard(ws->device);
   GemmDesc g{};
   g.M = n; g.N = n; g.K = n;
   g.A = W; g.lda = ldw; g.a_layout = OP_MC;
@@ -175,6 +211,7 @@ int munk_dgemm(munk_workspace_t* ws, int a_layout, int b_layout, int M, int N, i
                const double* A, long lda, const double* B, long ldb, double beta, double* C,
                long ldc, int flags, void* stream) {
   if (!ws) return -1;
+  DeviceGuard guard(ws->device);
   if ((a_layout | b_layout) & ~1) return -2;
   if (M < 0 || N < 0 || K < 0) return -4;
   GemmDesc g{};

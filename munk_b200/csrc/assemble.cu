@@ -14,21 +14,31 @@ namespace munk {
 
 namespace {
 
-__global__ void degree_kernel(int nnz, const int* __restrict__ u, const int* __restrict__ v,
-                              int* __restrict__ deg) {
+// An edge whose endpoints are not both in [0, n) is skipped and reported (first one wins) in
+// *bad as 1 + edge index: a caller of the C ABI cannot make the kernels write out of bounds.
+__global__ void degree_kernel(int n, int nnz, const int* __restrict__ u, const int* __restrict__ v,
+                              int* __restrict__ deg, int* __restrict__ bad) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < nnz) {
-    atomicAdd(deg + u[e], 1);
-    atomicAdd(deg + v[e], 1);
+    const int a = u[e], b = v[e];
+    if ((unsigned)a >= (unsigned)n || (unsigned)b >= (unsigned)n) {
+      atomicCAS(bad, 0, e + 1);
+      return;
+    }
+    atomicAdd(deg + a, 1);
+    atomicAdd(deg + b, 1);
   }
 }
 
 // One pass over the whole n x ld array: zeros, and the diagonal entry of each row.
 // Each thread stores 16 bytes; a block covers 4096 contiguous bytes of one row per step.
+// The diagonal of L is the integer degree (`deg`) or, for weighted graphs, the float64 diagonal
+// networkx computed (`ldiag`).
 __global__ void __launch_bounds__(256)
-fill_reglap_kernel(int n, long ld, double lam, const int* __restrict__ deg, double* __restrict__ A) {
+fill_reglap_kernel(int n, long ld, double lam, const int* __restrict__ deg,
+                   const double* __restrict__ ldiag, double* __restrict__ A) {
   const int row = blockIdx.x;
-  const double diag = __dadd_rn(1.0, __dmul_rn(lam, (double)deg[row]));
+  const double diag = __dadd_rn(1.0, __dmul_rn(lam, ldiag ? ldiag[row] : (double)deg[row]));
   double2* __restrict__ p = reinterpret_cast<double2*>(A + (long)row * ld);
   const int npair = (int)(ld >> 1);
   const int dpair = row >> 1;
@@ -41,12 +51,19 @@ fill_reglap_kernel(int n, long ld, double lam, const int* __restrict__ deg, doub
   }
 }
 
-__global__ void scatter_edges_kernel(int nnz, const int* __restrict__ u, const int* __restrict__ v,
-                                     double lam, long ld, double* __restrict__ A) {
+// lval == nullptr: unweighted, L[a][b] = -1.  Otherwise lval[e] is the off-diagonal Laplacian
+// entry itself (-weight, parallel edges already summed by the host).
+__global__ void scatter_edges_kernel(int n, int nnz, const int* __restrict__ u, const int* __restrict__ v,
+                                     const double* __restrict__ lval, double lam, long ld,
+                                     double* __restrict__ A, int* __restrict__ bad) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < nnz) {
-    const double w = __dmul_rn(lam, -1.0);
     const long a = u[e], b = v[e];
+    if ((unsigned long)a >= (unsigned long)n || (unsigned long)b >= (unsigned long)n) {
+      atomicCAS(bad, 0, e + 1);
+      return;
+    }
+    const double w = __dmul_rn(lam, lval ? lval[e] : -1.0);
     A[a * ld + b] = w;
     A[b * ld + a] = w;
   }
@@ -130,24 +147,27 @@ __global__ void gather_pairs_kernel(int npairs, const int* __restrict__ r, const
 
 }  // namespace
 
-int assemble_reglap(int n, int nnz, const int* u, const int* v, double lam, double* A, long ld,
-                    int* deg_scratch, cudaStream_t stream) {
+int assemble_reglap(int n, int nnz, const int* u, const int* v, const double* lval,
+                    const double* ldiag, double lam, double* A, long ld, int* deg_scratch, int* bad,
+                    cudaStream_t stream) {
   if (n <= 0) return MUNK_OK;
   if ((ld & 1) || ((uintptr_t)A & 15)) {
     set_last_error("assemble: A must be 16-byte aligned with an even leading dimension");
     return -7;
   }
-  MUNK_CUDA_TRY(cudaMemsetAsync(deg_scratch, 0, (size_t)n * sizeof(int), stream));
-  if (nnz > 0) {
-    degree_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(nnz, u, v, deg_scratch);
-    MUNK_CUDA_TRY(cudaGetLastError());
+  if (!ldiag) {
+    MUNK_CUDA_TRY(cudaMemsetAsync(deg_scratch, 0, (size_t)n * sizeof(int), stream));
+    if (nnz > 0) {
+      degree_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(n, nnz, u, v, deg_scratch, bad);
+      MUNK_CUDA_TRY(cudaGetLastError());
+    }
   }
   const int npair = (int)(ld >> 1);
   dim3 grid(n, std::min(16, (npair + 255) / 256));
-  fill_reglap_kernel<<<grid, 256, 0, stream>>>(n, ld, lam, deg_scratch, A);
+  fill_reglap_kernel<<<grid, 256, 0, stream>>>(n, ld, lam, deg_scratch, ldiag, A);
   MUNK_CUDA_TRY(cudaGetLastError());
   if (nnz > 0) {
-    scatter_edges_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(nnz, u, v, lam, ld, A);
+    scatter_edges_kernel<<<(nnz + 255) / 256, 256, 0, stream>>>(n, nnz, u, v, lval, lam, ld, A, bad);
     MUNK_CUDA_TRY(cudaGetLastError());
   }
   return MUNK_OK;

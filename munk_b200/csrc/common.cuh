@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #define MUNK_LEAF 128          // diagonal-block size of the recursive factorisations
+#define MUNK_MAX_DEVICES 64    // per-device "kernel attribute set" flags
 #define MUNK_OK 0
 
 // Status codes of the C ABI (see include/munk_b200.h).
@@ -34,6 +35,19 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 static inline long round_up(long x, long m) { return (x + m - 1) / m * m; }
+
+// Makes `device` current for the lifetime of the object (C-ABI entry points: a workspace belongs
+// to one device, the caller's current device may be another).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 // ---------------------------------------------------------------------------
 // Device-side PTX wrappers: mbarrier, TMA, DMMA.

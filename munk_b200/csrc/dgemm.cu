@@ -388,11 +388,13 @@ int make_operand_map(CUtensorMap* tm, const double* base, long ld, int layout, i
 template <bool A_KC, bool B_KC>
 int launch_variant(const CUtensorMap& ta, const CUtensorMap& tb, const KernelArgs& ka, dim3 grid,
                    cudaStream_t stream) {
-  static bool configured = false;
+  static bool configured[MUNK_MAX_DEVICES] = {};       // the attribute is per device
   auto kern = dgemm_dmma_tma_kernel<A_KC, B_KC>;
-  if (!configured) {
+  int dev = 0;
+  MUNK_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= MUNK_MAX_DEVICES || !configured[dev]) {
     MUNK_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+    if (dev < MUNK_MAX_DEVICES) configured[dev] = true;
   }
   kern<<<grid, GEMM_THREADS, SMEM_BYTES, stream>>>(ta, tb, ka);
   MUNK_CUDA_TRY(cudaGetLastError());

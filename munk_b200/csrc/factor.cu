@@ -14,13 +14,11 @@
 // One CTA factors a 128x128 diagonal block and also inverts it (leaf.cu); the inverse is kept
 // (`linv`) and turns the leaf trsm into a DMMA product and the leaf trtri into a copy.
 //
-// Large matrices use the right-looking blocked driver potrf_lookahead(): panels of 512 columns,
-// the panel work (look-ahead update of the next block column, its recursive factorisation and
-// panel solve: many small, latency-bound launches) runs on a high-priority side stream while the
-// caller's stream applies the previous panel to the rest of the trailing matrix (one big DMMA
-// syrk per panel), so the latency-bound part is hidden behind tensor-core work.
+// Large matrices use the right-looking blocked driver potrf_lookahead(): block columns of
+// 1024/512/256 columns, scheduled critical path first on three streams (see its comment).
 #include "dgemm.cuh"
 #include "factor.cuh"
+#include "factor_internal.cuh"
 #include "leaf.cuh"
 #include "workspace.cuh"
 
@@ -29,12 +27,10 @@
 
 namespace munk {
 
-namespace {
+namespace detail {
 
-constexpr int LEAF = MUNK_LEAF;
-constexpr int PANEL = 512;          // block-column width of the look-ahead driver ...
-constexpr int PANEL_SMALL = 256;    // ... once fewer than PANEL_SWITCH columns remain
-constexpr int PANEL_SWITCH = 8192;
+constexpr int PANEL = 512;          // default block-column width of the right-looking driver
+constexpr int PANEL_SMALL = 256;    // ... near the end of the matrix (see panel_starts)
 
 // dst (nb x nb block inside a row-major matrix) <- src (128-ld leaf inverse)
 __global__ void copy_leaf_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ src,
@@ -44,21 +40,6 @@ __global__ void copy_leaf_kernel(double* __restrict__ dst, long ldd, const doubl
     if (c < nb) dst[(long)r * ldd + c] = src[idx];
   }
 }
-
-// largest multiple of 128 that is <= n/2 rounded up, strictly inside (0, n)
-inline int split_point(int n) {
-  int h = (int)round_up((n + 1) / 2, LEAF);
-  if (h >= n) h -= LEAF;
-  return h;
-}
-
-struct Rec {
-  Workspace* ws;
-  cudaStream_t stream;
-  double* linv;      // leaf inverses of this matrix, block g at linv + g*128*128
-  int scratch;       // split-K buffer of `stream` (0 caller's stream, 1 side stream)
-  const int* stair = nullptr;   // forward left solve: first non-zero row of each 128-column RHS tile
-};
 
 int leaf_potrf(Rec& r, double* A, long ld, int nb, int gidx) {
   MUNK_TRY(launch_potrf_leaf(A, ld, nb, r.linv + (long)(gidx / LEAF) * LEAF * LEAF, gidx, r.ws->info,
@@ -115,105 +96,154 @@ int potrf_rec(Rec& r, double* A, long ld, int n, int gidx) {
   return potrf_rec(r, A22, ld, n2, gidx + n1);
 }
 
-// Right-looking blocked Cholesky with one panel of look-ahead on the side stream.
-//   step j (panel j = columns [c0, c0+w) already factored, event panel[j]):
-//     side stream : wait upd[j-1];  block column j+1 -= panel j contributions (look-ahead);
-//                   factor panel j+1 (potrf_rec of its diagonal block + trsm_rec below);
-//                   record panel[j+1]
-//     main stream : wait panel[j];  columns beyond block column j+1 -= panel j contributions
-//                   (one lower-tile DMMA syrk, K = w);  record upd[j]
-int potrf_lookahead(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t main) {
-  // Panel boundaries: 512 columns while the trailing matrix is large (each 128x128 tile of the
-  // trailing syrk then runs 32 k-iterations and amortises its prologue/epilogue), 256 columns
-  // once it is small, where the panel chain on the side stream is the critical path and a
-  // shorter chain (and shorter main-stream tiles to wait behind) matters more.  Measured on
-  // B200: n = 8192 13.3 -> 12.3 ms with 256 throughout, n = 20000 107 -> 127 ms.
+// C (m x nc) -= X (m x k) Y (nc x k)^T, every tile (rows strictly below the diagonal block).
+int gemm_update(Rec& r, double* C, long ldc, int m, int nc, const double* X, const double* Y, long ldx,
+                int k) {
+  if (m <= 0 || nc <= 0) return MUNK_OK;
+  GemmDesc g{};
+  g.M = m; g.N = nc; g.K = k;
+  g.A = X; g.lda = ldx; g.a_layout = OP_KC;
+  g.B = Y; g.ldb = ldx; g.b_layout = OP_KC;
+  g.C = C; g.ldc = ldc;
+  g.alpha = -1.0; g.beta = 1.0; g.flags = 0;
+  return gemm_launch(r.ws, g, r.stream, r.scratch);
+}
+
+// Block-column boundaries of the right-looking driver: wide panels while the trailing matrix is
+// large (each 128x128 tile of the trailing update then runs K/16 k-iterations and amortises its
+// ~5.5 us of prologue/epilogue), narrower ones towards the end, where the diagonal-block chain is
+// the critical path.  All multiples of 128.
+std::vector<int> panel_starts(int n) {
+  static const int big = env_int("MUNK_PANEL_BIG", 1024), big_until = env_int("MUNK_PANEL_BIG_UNTIL", 12288);
+  static const int mid = env_int("MUNK_PANEL", PANEL), small = env_int("MUNK_PANEL_SMALL", PANEL_SMALL);
+  static const int small_from = env_int("MUNK_PANEL_SWITCH", 4096);
   std::vector<int> start;
   for (int c = 0; c < n;) {
     start.push_back(c);
-    c += (n - c > PANEL_SWITCH) ? PANEL : PANEL_SMALL;
+    const int rem = n - c;
+    c += rem > big_until ? big : (rem > small_from ? mid : small);
   }
   start.push_back(n);
-  const int nblk = (int)start.size() - 1;
-  MUNK_TRY(ws->ensure_side(2 * (size_t)nblk + 2));
-  MUNK_TRY(ws->ensure_splitk(0, SPLITK_RESERVE));
-  MUNK_TRY(ws->ensure_splitk(1, SPLITK_RESERVE));
-  cudaStream_t side = ws->side;
-  cudaEvent_t* panel_ev = ws->events.data();          // [nblk]
-  cudaEvent_t* upd_ev = ws->events.data() + nblk;     // [nblk]
-  cudaEvent_t fork_ev = ws->events[2 * nblk];
-  Rec rs{ws, side, linv, 1}, rm{ws, main, linv, 0};
+  return start;
+}
 
-  auto factor_panel = [&](int c0, int w) -> int {
-    double* diag = A + (long)c0 * ld + c0;
-    MUNK_TRY(potrf_rec(rs, diag, ld, w, c0));
-    const int below = n - (c0 + w);
-    if (below > 0) MUNK_TRY(trsm_rec(rs, diag + (long)w * ld, ld, below, diag, ld, w, c0));
-    return MUNK_OK;
+// Right-looking blocked Cholesky, critical path first.  Block column c has diagonal rows
+// D(c) = [s_c, s_c+1), next rows N(c) = [s_c+1, s_c+2) and rest R(c) = [s_c+2, n); P_c is its
+// finished panel.  Tasks (all "-=" below are DMMA products with K = width of the earlier panel):
+//   LA_D(c)  A[D(c),c] -= P_c-1[D(c)] P_c-1[D(c)]^T      LA_N/LA_R(c) the same for rows N(c)/R(c)
+//   F(c)     Cholesky (+ leaf inverses) of the diagonal block
+//   TS_N(c)  A[N(c),c] <- A[N(c),c] L_cc^-T               TS_R(c) the same for rows R(c)
+//   T(c)     A[R(c), columns >= s_c+2] -= P_c[R(c)] P_c[R(c)]^T   (the bulk of the flops)
+// The only serial chain of the factorisation is F(c) -> TS_N(c) -> LA_D(c+1) -> F(c+1): three
+// small tasks per block column.  It gets its own highest-priority stream (`side`); everything
+// else that feeds it (TS_R, LA_N, LA_R: tall GEMMs over the rows below) runs on a second stream
+// one priority level lower (`side2`), rows needed first launched first, and overlaps the
+// latency-bound F(c); the caller's stream runs T(c).  Round 1 had LA(whole column), F and
+// TS(whole column) in series on one stream: ~1.3 ms per block column against ~0.4 ms now.
+//   side : [upd c-2] LA_D(c)  F(c)  (diag c)  [lan c] TS_N(c)  (tsn c)
+//   side2: [diag c] TS(N(c+1) rows)  [tsn c][upd c-1] LA_N(c+1) (lan c+1)  TS(rest)  (panel c)  LA_R(c+1)
+//   main : [panel c] T(c) (upd c)                         [x] = wait event, (x) = record event
+int potrf_lookahead(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t main) {
+  const std::vector<int> start = panel_starts(n);
+  const int nblk = (int)start.size() - 1;
+  MUNK_TRY(ws->ensure_side(5 * (size_t)nblk + 2));
+  for (int i = 0; i < 3; ++i) MUNK_TRY(ws->ensure_splitk(i, SPLITK_RESERVE));
+  cudaStream_t side = ws->side, side2 = ws->side2;
+  cudaEvent_t* diag_ev = ws->events.data();             // F(c) done
+  cudaEvent_t* tsn_ev = diag_ev + nblk;                 // TS_N(c) done
+  cudaEvent_t* lan_ev = tsn_ev + nblk;                  // LA_N(c) done
+  cudaEvent_t* panel_ev = lan_ev + nblk;                // all of P_c done
+  cudaEvent_t* upd_ev = panel_ev + nblk;                // T(c) done
+  cudaEvent_t fork_ev = ws->events[5 * nblk], join_ev = ws->events[5 * nblk + 1];
+  Rec rs{ws, side, linv, 1}, rp{ws, side2, linv, 2}, rm{ws, main, linv, 0};
+  auto s = [&](int c) { return start[std::min(c, nblk)]; };
+  auto at = [&](int row, int col) { return A + (long)row * ld + col; };
+  // A[r0:r1, block column c] -= P_c-1[r0:r1] P_c-1[D(c)]^T
+  auto la = [&](Rec& r, int r0, int r1, int c) -> int {
+    const int k = s(c) - s(c - 1), w = s(c + 1) - s(c);
+    if (r0 == s(c)) return syrk_update(r, at(r0, s(c)), ld, r1 - r0, w, at(r0, s(c - 1)), at(s(c), s(c - 1)), ld, k);
+    return gemm_update(r, at(r0, s(c)), ld, r1 - r0, w, at(r0, s(c - 1)), at(s(c), s(c - 1)), ld, k);
+  };
+  // A[r0:r1, block column c] <- . L_cc^-T
+  auto ts = [&](Rec& r, int r0, int r1, int c) -> int {
+    return trsm_rec(r, at(r0, s(c)), ld, r1 - r0, at(s(c), s(c)), ld, s(c + 1) - s(c), s(c));
   };
 
   MUNK_CUDA_TRY(cudaEventRecord(fork_ev, main));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(side, fork_ev, 0));
-  MUNK_TRY(factor_panel(0, start[1]));
-  MUNK_CUDA_TRY(cudaEventRecord(panel_ev[0], side));
+  MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, fork_ev, 0));
 
-  // MUNK_TRACE_POTRF=1: per-step device timeline (diagnostics only; synchronises at the end)
+  // MUNK_TRACE_POTRF=1: per-column device timeline of the chain stream (diagnostics only)
   const bool trace = getenv("MUNK_TRACE_POTRF") != nullptr;
-  std::vector<cudaEvent_t> tm0, tm1, ts0, ts1, ts2;
-  auto tick = [&](std::vector<cudaEvent_t>& v, cudaStream_t s) {
+  std::vector<cudaEvent_t> tr;
+  auto tick = [&](cudaStream_t st) {
     if (!trace) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
-    cudaEventRecord(e, s);
-    v.push_back(e);
+    cudaEventRecord(e, st);
+    tr.push_back(e);
   };
 
-  int last_panel = 0;
-  for (int j = 0; j + 1 < nblk; ++j) {
-    const int c0 = start[j], w = start[j + 1] - c0;
-    const int r1 = c0 + w;                            // first row/column of block column j+1
-    const int w1 = start[j + 2] - r1;
-    const int r2 = r1 + w1;                           // first column the main stream updates
-    const double* pan = A + (long)r1 * ld + c0;       // panel j rows >= r1
-    // side: look-ahead update of block column j+1, then its factorisation
-    if (j > 0) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, upd_ev[j - 1], 0));
-    tick(ts0, side);
-    MUNK_TRY(syrk_update(rs, A + (long)r1 * ld + r1, ld, n - r1, w1, pan, pan, ld, w));
-    tick(ts1, side);
-    MUNK_TRY(factor_panel(r1, w1));
-    tick(ts2, side);
-    MUNK_CUDA_TRY(cudaEventRecord(panel_ev[j + 1], side));
-    last_panel = j + 1;
-    // main: the rest of the trailing matrix
-    MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[j], 0));
-    tick(tm0, main);
-    if (r2 < n) {
-      const double* pan2 = A + (long)r2 * ld + c0;    // panel j rows >= r2
-      MUNK_TRY(syrk_update(rm, A + (long)r2 * ld + r2, ld, n - r2, n - r2, pan2, pan2, ld, w));
+  for (int c = 0; c < nblk; ++c) {
+    // ---- chain: LA_D(c), F(c), TS_N(c)
+    if (c >= 2) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, upd_ev[c - 2], 0));
+    tick(side);
+    if (c >= 1) MUNK_TRY(la(rs, s(c), s(c + 1), c));
+    tick(side);
+    MUNK_TRY(potrf_rec(rs, at(s(c), s(c)), ld, s(c + 1) - s(c), s(c)));
+    MUNK_CUDA_TRY(cudaEventRecord(diag_ev[c], side));
+    tick(side);
+    if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, lan_ev[c], 0));
+    if (c + 1 < nblk) MUNK_TRY(ts(rs, s(c + 1), s(c + 2), c));
+    MUNK_CUDA_TRY(cudaEventRecord(tsn_ev[c], side));
+    tick(side);
+    // ---- panel stream: the rest of P_c, then the look-ahead updates of block column c + 1
+    MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, diag_ev[c], 0));
+    if (c + 2 < nblk) MUNK_TRY(ts(rp, s(c + 2), s(c + 3), c));
+    MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, tsn_ev[c], 0));
+    if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, upd_ev[c - 1], 0));
+    if (c + 2 < nblk) MUNK_TRY(la(rp, s(c + 2), s(c + 3), c + 1));
+    if (c + 1 < nblk) MUNK_CUDA_TRY(cudaEventRecord(lan_ev[c + 1], side2));
+    if (c + 3 < nblk) MUNK_TRY(ts(rp, s(c + 3), n, c));
+    MUNK_CUDA_TRY(cudaEventRecord(panel_ev[c], side2));
+    if (c + 3 < nblk) MUNK_TRY(la(rp, s(c + 3), n, c + 1));
+    // ---- caller's stream: the trailing update beyond block column c + 1
+    MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[c], 0));
+    if (c + 2 < nblk) {
+      const int r2 = s(c + 2);
+      MUNK_TRY(syrk_update(rm, at(r2, r2), ld, n - r2, n - r2, at(r2, s(c)), at(r2, s(c)), ld, s(c + 1) - s(c)));
     }
-    tick(tm1, main);
-    MUNK_CUDA_TRY(cudaEventRecord(upd_ev[j], main));
+    MUNK_CUDA_TRY(cudaEventRecord(upd_ev[c], main));
   }
-  MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[last_panel], 0));   // join
+  MUNK_CUDA_TRY(cudaEventRecord(join_ev, side));
+  MUNK_CUDA_TRY(cudaStreamWaitEvent(main, join_ev, 0));           // side2 joined through panel_ev
   if (trace) {
     cudaStreamSynchronize(main);
-    fprintf(stderr, "potrf_lookahead n=%d: step rem | main: start dur | side: start lookahead panel (ms)\n", n);
-    for (size_t j = 0; j < tm0.size(); ++j) {
-      float a = 0, b = 0, c = 0, d = 0, e = 0;
-      cudaEventElapsedTime(&a, tm0[0], tm0[j]);
-      cudaEventElapsedTime(&b, tm0[j], tm1[j]);
-      cudaEventElapsedTime(&c, tm0[0], ts0[j]);
-      cudaEventElapsedTime(&d, ts0[j], ts1[j]);
-      cudaEventElapsedTime(&e, ts1[j], ts2[j]);
-      fprintf(stderr, "  %3zu %6d | %8.3f %7.3f | %8.3f %7.3f %7.3f\n", j, n - start[j + 1], a, b, c, d, e);
+    fprintf(stderr, "potrf n=%d: col rem | chain start, LA_D, F, wait+TS_N (ms)\n", n);
+    for (int c = 0; c < nblk; ++c) {
+      float t0 = 0, a = 0, b = 0, d = 0;
+      cudaEventElapsedTime(&t0, tr[0], tr[4 * c]);
+      cudaEventElapsedTime(&a, tr[4 * c], tr[4 * c + 1]);
+      cudaEventElapsedTime(&b, tr[4 * c + 1], tr[4 * c + 2]);
+      cudaEventElapsedTime(&d, tr[4 * c + 2], tr[4 * c + 3]);
+      fprintf(stderr, "  %3d %6d | %8.3f %7.3f %7.3f %7.3f\n", c, n - start[c], t0, a, b, d);
     }
-    for (auto* v : {&tm0, &tm1, &ts0, &ts1, &ts2})
-      for (cudaEvent_t ev : *v) cudaEventDestroy(ev);
+    for (cudaEvent_t e : tr) cudaEventDestroy(e);
   }
   return MUNK_OK;
 }
 
-int trtri_rec(Rec& r, double* L, long ld, int n, int gidx) {
+// Triangular inverse by recursive halving.  The two half-size sub-inversions are independent:
+// down to `fork_depth` levels the second one runs on a pool stream (own split-K scratch, its own
+// half of the temporary), so up to 8 subtrees are in flight and their small, latency-bound
+// products and leaf copies overlap instead of queueing on one stream.
+struct TrtriCtx {
+  int next_pool = 0;        // pool streams handed out so far
+  size_t next_event;        // events handed out so far (index into ws->events)
+};
+
+int trtri_rec(Rec& r, TrtriCtx& cx, double* L, long ld, int n, int gidx, double* tmp, size_t tmp_elems,
+              int depth) {
   if (n <= LEAF) {
     copy_leaf_kernel<<<16, 256, 0, r.stream>>>(L, ld, r.linv + (long)(gidx / LEAF) * LEAF * LEAF, n);
     MUNK_CUDA_TRY(cudaGetLastError());
@@ -221,23 +251,47 @@ int trtri_rec(Rec& r, double* L, long ld, int n, int gidx) {
     return MUNK_OK;
   }
   const int n1 = split_point(n), n2 = n - n1;
-  MUNK_TRY(trtri_rec(r, L, ld, n1, gidx));
-  MUNK_TRY(trtri_rec(r, L + (long)n1 * ld + n1, ld, n2, gidx + n1));
+  static const int fork_depth = env_int("MUNK_TRTRI_FORK_DEPTH", 3);
+  const bool fork = depth < fork_depth && n >= 1024 && cx.next_pool < POOL_STREAMS;
+  if (fork) {
+    const int pi = cx.next_pool++;
+    Rec r2 = r;
+    r2.stream = r.ws->pool[pi];
+    r2.scratch = 3 + pi;
+    MUNK_TRY(r.ws->ensure_splitk(r2.scratch, SPLITK_RESERVE));
+    MUNK_TRY(r.ws->ensure_events(cx.next_event + 2));
+    cudaEvent_t f = r.ws->events[cx.next_event++], j = r.ws->events[cx.next_event++];
+    MUNK_CUDA_TRY(cudaEventRecord(f, r.stream));
+    MUNK_CUDA_TRY(cudaStreamWaitEvent(r2.stream, f, 0));
+    const size_t half = tmp_elems / 2 / 2 * 2;          // keeps 16-byte alignment
+    MUNK_TRY(trtri_rec(r, cx, L, ld, n1, gidx, tmp, half, depth + 1));
+    MUNK_TRY(trtri_rec(r2, cx, L + (long)n1 * ld + n1, ld, n2, gidx + n1, tmp + half, half, depth + 1));
+    MUNK_CUDA_TRY(cudaEventRecord(j, r2.stream));
+    MUNK_CUDA_TRY(cudaStreamWaitEvent(r.stream, j, 0));
+  } else {
+    MUNK_TRY(trtri_rec(r, cx, L, ld, n1, gidx, tmp, tmp_elems, depth + 1));
+    MUNK_TRY(trtri_rec(r, cx, L + (long)n1 * ld + n1, ld, n2, gidx + n1, tmp, tmp_elems, depth + 1));
+  }
   double* L21 = L + (long)n1 * ld;
   const long ldt = round_up(n1, 16);
+  if ((size_t)n2 * ldt > tmp_elems) {
+    set_last_error("trtri temporary too small (%d x %ld needs %zu elements, have %zu)", n2, ldt,
+                   (size_t)n2 * ldt, tmp_elems);
+    return -20;
+  }
   // T = L21 * W11   (W11 lower: k >= column)
   GemmDesc g{};
   g.M = n2; g.N = n1; g.K = n1;
   g.A = L21; g.lda = ld; g.a_layout = OP_KC;
   g.B = L; g.ldb = ld; g.b_layout = OP_MC;
-  g.C = r.ws->tmp; g.ldc = ldt;
+  g.C = tmp; g.ldc = ldt;
   g.alpha = 1.0; g.beta = 0.0; g.flags = GF_KLO_N;
   MUNK_TRY(gemm_launch(r.ws, g, r.stream, r.scratch));
   // W21 = -W22 * T  (W22 lower: k <= row)
   GemmDesc h{};
   h.M = n2; h.N = n1; h.K = n2;
   h.A = L + (long)n1 * ld + n1; h.lda = ld; h.a_layout = OP_KC;
-  h.B = r.ws->tmp; h.ldb = ldt; h.b_layout = OP_MC;
+  h.B = tmp; h.ldb = ldt; h.b_layout = OP_MC;
   h.C = L21; h.ldc = ld;
   h.alpha = -1.0; h.beta = 0.0; h.flags = GF_KHI_M;
   return gemm_launch(r.ws, h, r.stream, r.scratch);
@@ -258,7 +312,7 @@ int trsm_left_rec(Rec& r, const double* L, long ldl, int n, double* B, long ldb,
     g.B = B; g.ldb = ldb; g.b_layout = OP_MC;
     g.C = B; g.ldc = ldb;
     g.alpha = 1.0; g.beta = 0.0; g.flags = transposed ? GF_KLO_M : GF_KHI_M;
-    if (!transposed && r.stair) { g.stair_n = r.stair; g.stair_row0 = gidx; g.stair_k0 = gidx; }
+    if (!transposed && r.stair) { g.stair_n = r.stair; g.stair_row0 = r.stair_base + gidx; g.stair_k0 = r.stair_base + gidx; }
     return gemm_launch(r.ws, g, r.stream, r.scratch);
   }
   const int n1 = split_point(n), n2 = n - n1;
@@ -272,7 +326,7 @@ int trsm_left_rec(Rec& r, const double* L, long ldl, int n, double* B, long ldb,
   if (!transposed) {
     MUNK_TRY(trsm_left_rec(r, L, ldl, n1, B, ldb, nrhs, gidx, false));
     g.M = n2; g.K = n1; g.a_layout = OP_KC; g.B = B; g.C = B2;          // B2 -= L21 X1
-    if (r.stair) { g.stair_n = r.stair; g.stair_row0 = gidx + n1; g.stair_k0 = gidx; }
+    if (r.stair) { g.stair_n = r.stair; g.stair_row0 = r.stair_base + gidx + n1; g.stair_k0 = r.stair_base + gidx; }
     MUNK_TRY(gemm_launch(r.ws, g, r.stream, r.scratch));
     return trsm_left_rec(r, L22, ldl, n2, B2, ldb, nrhs, gidx + n1, false);
   }
@@ -282,7 +336,9 @@ int trsm_left_rec(Rec& r, const double* L, long ldl, int n, double* B, long ldb,
   return trsm_left_rec(r, L, ldl, n1, B, ldb, nrhs, gidx, true);
 }
 
-}  // namespace
+}  // namespace detail
+
+using namespace detail;
 
 int trsm_left(Workspace* ws, int n, const double* L, long ld, const double* linv, int transposed,
               int nrhs, double* B, long ldb, const int* stair, cudaStream_t stream) {
@@ -301,23 +357,122 @@ int trsm_right(Workspace* ws, int m, double* B, long ldb, const double* L, long 
 
 size_t linv_bytes_for(int n) { return (size_t)((n + LEAF - 1) / LEAF) * LEAF * LEAF * 8; }
 
-int potrf_lower(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t stream) {
-  if (n <= 0) return MUNK_OK;
+namespace {
+
+int potrf_direct(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t stream) {
   if (n > 2 * PANEL) return potrf_lookahead(ws, n, A, ld, linv, stream);
   Rec r{ws, stream, linv, 0};
   return potrf_rec(r, A, ld, n, 0);
 }
 
-int trtri_lower(Workspace* ws, int n, double* L, long ld, double* linv, cudaStream_t stream) {
-  if (n <= 0) return MUNK_OK;
+int trtri_direct(Workspace* ws, int n, double* L, long ld, double* linv, cudaStream_t stream) {
+  size_t elems = 0;
   if (n > LEAF) {
+    // the top-level temporary (n2 x n1) is the largest of the recursion; a forked level gives
+    // each half of it to one sub-inversion, whose own temporary is a quarter of that size
     const int n1 = split_point(n);
-    const size_t need = (size_t)(n - n1) * round_up(n1, 16) * 8;
-    // the top-level temporary is the largest one of the recursion (n2 <= n1 at every level)
-    MUNK_TRY(ws->ensure(&ws->tmp, &ws->tmp_bytes, std::max(need, (size_t)n1 * round_up(n1, 16) * 8)));
+    elems = std::max((size_t)(n - n1) * round_up(n1, 16), (size_t)n1 * round_up(n1, 16));
+    MUNK_TRY(ws->ensure(&ws->tmp, &ws->tmp_bytes, elems * 8));
+    MUNK_TRY(ws->ensure_pool(stream));
+    MUNK_TRY(ws->ensure_splitk(0, SPLITK_RESERVE));
   }
   Rec r{ws, stream, linv, 0};
-  return trtri_rec(r, L, ld, n, 0);
+  TrtriCtx cx;
+  cx.next_event = 0;
+  return trtri_rec(r, cx, L, ld, n, 0, ws->tmp, elems, 0);
+}
+
+constexpr int GRAPH_MIN_N = 4096;      // below this the direct path costs the host < 3 ms
+constexpr size_t GRAPH_CACHE = 8;
+
+// Runs `direct` (op 0 = potrf, 1 = trtri) either directly or as a cached CUDA graph.  First use
+// of a (op, n, pointers) key: direct, which also performs every allocation and kernel-attribute
+// call (none may happen inside a capture).  Second use: captured from `stream` - the side and
+// pool streams join the capture through the fork event - instantiated and launched.  Later
+// uses: one cudaGraphLaunch.  The temporary of trtri is part of the key's validity: it only
+// grows, and growing it (a larger n) drops the cached graphs.
+template <typename F>
+int graph_or_direct(Workspace* ws, int op, int n, double* A, long ld, double* linv, cudaStream_t stream,
+                    F direct) {
+  static const bool off = getenv("MUNK_NO_GRAPH") != nullptr;
+  if (off || n < GRAPH_MIN_N || getenv("MUNK_TRACE_POTRF")) return direct();
+  // the legacy / per-thread default streams cannot be captured
+  if (stream == nullptr || stream == cudaStreamLegacy || stream == cudaStreamPerThread) return direct();
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return direct();                       // the caller is capturing already: just record into it
+  }
+  Workspace::GraphEntry* hit = nullptr;
+  for (auto& g : ws->graphs)
+    if (g.op == op && g.n == n && g.a == A && g.ld == ld && g.linv == linv) hit = &g;
+  if (!hit) {
+    if (ws->graphs.size() >= GRAPH_CACHE) {
+      size_t old = 0;
+      for (size_t i = 1; i < ws->graphs.size(); ++i)
+        if (ws->graphs[i].stamp < ws->graphs[old].stamp) old = i;
+      if (ws->graphs[old].exec) cudaGraphExecDestroy(ws->graphs[old].exec);
+      ws->graphs.erase(ws->graphs.begin() + old);
+    }
+    ws->graphs.push_back({op, n, A, ld, linv, nullptr, 0, 0.0, ++ws->graph_clock});
+    return direct();
+  }
+  hit->stamp = ++ws->graph_clock;
+  if (!hit->exec) {
+    const double* tmp_before = ws->tmp;
+    const long l0 = ws->launches;
+    const double f0 = ws->flops;
+    MUNK_CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    const int st = direct();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(stream, &graph);
+    if (st != MUNK_OK || e != cudaSuccess || !graph || ws->tmp != tmp_before) {
+      if (getenv("MUNK_GRAPH_DEBUG"))
+        fprintf(stderr, "munk: graph capture of op %d n=%d failed (status %d, %s)\n", op, n, st,
+                cudaGetErrorString(e));
+      if (graph) cudaGraphDestroy(graph);
+      (void)cudaGetLastError();
+      ws->launches = l0; ws->flops = f0;
+      hit->op = -1;                        // never try this key again
+      if (st != MUNK_OK) return st;
+      return direct();
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      if (getenv("MUNK_GRAPH_DEBUG"))
+        fprintf(stderr, "munk: graph instantiation of op %d n=%d failed (%s)\n", op, n, cudaGetErrorString(ie));
+      (void)cudaGetLastError();
+      ws->launches = l0; ws->flops = f0;
+      hit->op = -1;
+      return direct();
+    }
+    if (getenv("MUNK_GRAPH_DEBUG"))
+      fprintf(stderr, "munk: captured op %d n=%d into a graph (%ld launches)\n", op, n, ws->launches - l0);
+    hit->exec = exec;
+    hit->launches = ws->launches - l0;
+    hit->flops = ws->flops - f0;
+    ws->launches = l0; ws->flops = f0;
+  }
+  MUNK_CUDA_TRY(cudaGraphLaunch(hit->exec, stream));
+  ws->launches += hit->launches;
+  ws->flops += hit->flops;
+  return MUNK_OK;
+}
+
+}  // namespace
+
+int potrf_lower(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t stream) {
+  if (n <= 0) return MUNK_OK;
+  return graph_or_direct(ws, 0, n, A, ld, linv, stream,
+                         [&] { return potrf_direct(ws, n, A, ld, linv, stream); });
+}
+
+int trtri_lower(Workspace* ws, int n, double* L, long ld, double* linv, cudaStream_t stream) {
+  if (n <= 0) return MUNK_OK;
+  return graph_or_direct(ws, 1, n, L, ld, linv, stream,
+                         [&] { return trtri_direct(ws, n, L, ld, linv, stream); });
 }
 
 }  // namespace munk

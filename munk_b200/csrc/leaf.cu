@@ -190,11 +190,13 @@ potrf_leaf_kernel(double* __restrict__ A, long lda, int nb, double* __restrict__
 
 int launch_potrf_leaf(double* A, long lda, int nb, double* Linv, int gidx, int* info,
                       cudaStream_t stream) {
-  static bool configured = false;
+  static bool configured[MUNK_MAX_DEVICES] = {};       // the attribute is per device
   const int smem = (NB * LDM + 64 * LDT) * 8;
-  if (!configured) {
+  int dev = 0;
+  MUNK_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= MUNK_MAX_DEVICES || !configured[dev]) {
     MUNK_CUDA_TRY(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    if (dev < MUNK_MAX_DEVICES) configured[dev] = true;
   }
   potrf_leaf_kernel<<<1, LEAF_THREADS, smem, stream>>>(A, lda, nb, Linv, gidx, info);
   MUNK_CUDA_TRY(cudaGetLastError());

@@ -104,13 +104,40 @@ class Device:
                              _ptr(B), B.stride(0), beta, _ptr(C), C.stride(0), flags, self.stream()),
               "munk_dgemm")
 
-    def assemble(self, n, edges_u, edges_v, lam, out=None):
-        """A = I + lam*L from int32 edge index arrays (host or device)."""
+    def assemble(self, n, edges_u, edges_v, lam, out=None, lval=None, ldiag=None):
+        """A = I + lam*L from int32 edge index arrays (host or device).  lval/ldiag (float64, host
+        or device): the Laplacian's off-diagonal / diagonal entries for weighted graphs and
+        multigraphs (util.edge_index_arrays returns them as a 4-tuple)."""
         u, v = self.ints(edges_u), self.ints(edges_v)
         A = self.empty(n, n) if out is None else out
-        check(lib.munk_assemble_reglap(self._ws, n, int(u.numel()), _ptr(u), _ptr(v), float(lam),
-                                       _ptr(A), A.stride(0), self.stream()), "munk_assemble_reglap")
+        if lval is None:
+            check(lib.munk_assemble_reglap(self._ws, n, int(u.numel()), _ptr(u), _ptr(v), float(lam),
+                                           _ptr(A), A.stride(0), self.stream()), "munk_assemble_reglap")
+        else:
+            w, d = self.doubles(lval), self.doubles(ldiag)
+            assert int(w.numel()) == int(u.numel()) and int(d.numel()) == n
+            check(lib.munk_assemble_reglap_entries(self._ws, n, int(u.numel()), _ptr(u), _ptr(v), _ptr(w),
+                                                   _ptr(d), float(lam), _ptr(A), A.stride(0), self.stream()),
+                  "munk_assemble_reglap_entries")
         return A
+
+    def assemble_edges(self, n, edges, lam, out=None):
+        """assemble() for an `edges` tuple: (u, v) or (u, v, lval, ldiag)."""
+        if len(edges) == 2:
+            return self.assemble(n, edges[0], edges[1], lam, out=out)
+        return self.assemble(n, edges[0], edges[1], lam, out=out, lval=edges[2], ldiag=edges[3])
+
+    def assemble_info(self):
+        """1 + index of the first edge the assembly skipped as out of range (0 = none); synchronises."""
+        bad = ctypes.c_int(0)
+        check(lib.munk_assemble_info(self._ws, ctypes.byref(bad), self.stream()), "munk_assemble_info")
+        return bad.value
+
+    def doubles(self, values):
+        if torch.is_tensor(values):
+            return values if values.is_cuda else values.to(self.torch_device, non_blocking=True)
+        arr = np.ascontiguousarray(np.asarray(values, dtype=np.float64))
+        return torch.from_numpy(arr).to(self.torch_device)
 
     def new_linv(self, n):
         return torch.empty(lib.munk_linv_bytes(int(n)) // 8, dtype=torch.float64, device=self.torch_device)
@@ -214,80 +241,93 @@ class Device:
         A = self.assemble(n, edges_u, edges_v, lam)
         return self.inverse_factor(A, n)
 
-    def spd_solve_gram(self, G, k, B, ncols, weights=None):
-        """Z = pinv(G) B for the small k x k landmark Gram matrix (overwritten).
+    def kernel_factor_edges(self, n, edges, lam):
+        return self.inverse_factor(self.assemble_edges(n, edges, lam), n)
 
-        Fast path: Cholesky (G is SPD with a modest condition number whenever the landmark rows
-        are distinct rows of a kernel factor).  If a pivot is not positive, or the pivots span
-        more than ~3.5 decades (cond(G) beyond ~1e7, where a Cholesky solve could no longer meet
-        the 1e-8 score tolerance), the rank-revealing Jacobi solve (munk_sym_pinv_solve) takes
-        over and truncates the null space like np.linalg.pinv does.  self.last_rank holds the
-        rank that was used."""
-        G0 = G.clone()
-        linv = self.potrf(G, k, check_info=False)
-        bad = self.potrf_info()
-        if not bad:
-            d = torch.diagonal(G[:k, :k])
-            ratio = float((d.min() / d.max()) ** 2)
-            bad = not (ratio > 1e-7)
-        if bad:
-            if weights is None:
-                return self.sym_pinv_solve(G0, k, B, ncols)
-            # A source landmark listed c times counts c-fold in pinv's least-squares objective:
-            # pinv(M) B = pinv(D M') (D mean(B)) with D = diag(sqrt(c)).  (With full row rank the
-            # residual is zero and D drops out, which is why the Cholesky path ignores it.)
-            d = torch.sqrt(torch.as_tensor(np.asarray(weights, dtype=np.float64), device=self.torch_device))
-            G0[:k, :k] *= d[:, None] * d[None, :]
-            Bw = B.clone()
-            Bw[:k] *= d[:, None]
-            Z = self.sym_pinv_solve(G0, k, Bw, ncols)
-            Z[:k] *= d[:, None]
-            return Z
-        self.last_rank = k
-        Wg = self.trtri(G, k, linv)
-        Y = self.empty(k, ncols)
-        self.gemm(KC, MC, k, ncols, k, 1.0, Wg, B, 0.0, Y, KHI_M)      # Y = Wg B
-        Z = self.empty(k, ncols)
-        self.gemm(MC, MC, k, ncols, k, 1.0, Wg, Y, 0.0, Z, KLO_M)      # Z = Wg^T Y
-        return Z
+    # ---- landmark projection: np.linalg.pinv(source_C[source_idxs,:]).dot(target_D[target_idxs,:]) --
+    COND_LIMIT = 1e6      # largest cond(M M^T) the Gram/Cholesky path may be used for (error ~ cond * eps)
 
-    def sym_pinv_solve(self, G, k, B, ncols, rcond=1e-15):
-        """Z = pinv(G) B by the device Jacobi eigen-solver (G overwritten)."""
-        Z = self.empty(k, ncols)
-        work = torch.empty(lib.munk_sym_pinv_work_bytes(k, ncols) // 8 + 2, dtype=torch.float64,
-                           device=self.torch_device)
-        rank = ctypes.c_int(0)
-        check(lib.munk_sym_pinv_solve(self._ws, k, _ptr(G), G.stride(0), ncols, _ptr(B), B.stride(0),
-                                      _ptr(Z), Z.stride(0), _ptr(work), rcond, ctypes.byref(rank),
-                                      self.stream()), "munk_sym_pinv_solve")
-        self.last_rank = rank.value
-        return Z
-
-    def project(self, Q1, n1, B, n2, groups):
-        """P = C2hat^T = pinv(M) B with M^T = Q1 (n1 x k'), B = D2[Lt,:] (k x n2).
+    def project(self, Q1, n1, B, n2, groups, defer=False):
+        """P = C2hat^T = pinv(M) B with M^T = Q1 (n1 x k'), B = D2[Lt,:] (k x n2)  (munk.py:108-110).
 
         `groups` = (gptr, members) folds rows of B that belong to the same (duplicated) source
         landmark: np.linalg.pinv's least-squares / minimum-norm answer for duplicate rows of M
-        equals the answer for the de-duplicated M with the rows of B averaged.  With distinct
-        rows M M^T = D1[Ls,Ls] is a principal submatrix of an SPD matrix, so it is SPD with
-        condition <= cond(D1) and the Gram/Cholesky route is the exact pinv.
-        """
-        Z, kq = self.landmark_solve(Q1, n1, B, n2, groups)
+        equals the answer for the de-duplicated M with the rows of B averaged.
+
+        Fast path, always enqueued: G = M M^T, Cholesky, P = M^T G^-1 B.  With distinct rows of a
+        kernel factor G = D1[Ls,Ls] is a principal block of an SPD matrix, cond(G) <= cond(D1), and
+        this IS the pseudo-inverse.  Whether it was safe is decided on the device, without a host
+        synchronisation: `bad` = Cholesky failed, or the rigorous bound
+        |G|_F |G^-1|_F >= cond_2(G) exceeds COND_LIMIT.  If it was not, the robust path
+        (munk_pinv_rows_solve: one-sided Jacobi on the rows of M, numpy's rcond * sigma_max cut)
+        recomputes P.  defer=False checks the flag now (one synchronisation) and returns P;
+        defer=True returns (P, check) and the caller calls check.resolve() at its own
+        synchronisation point (it returns the final P)."""
+        Z, kq, check = self.landmark_solve(Q1, n1, B, n2, groups)
         P = self.empty(n1, n2)
         self.gemm(KC, MC, n1, n2, kq, 1.0, Q1, Z, 0.0, P, 0)           # P = M^T Z
-        return P
+        check.P = P
+        if defer:
+            return P, check
+        return check.resolve()
 
     def landmark_solve(self, Q1, n1, B, n2, groups):
-        """Z = (M M^T)^-1 mean_groups(B)  (k' x n2) and k', the factor shared by `project`
-        (P = M^T Z) and by the rank-k statistic (S = D1[:,Ls] Z)."""
+        """Fast path only: Z = (M M^T)^-1 mean_groups(B) (k' x n2), k' and the ProjectionCheck that
+        says whether Z may be used (shared by `project` and the rank-k statistic S = D1[:,Ls] Z)."""
         gptr, members = groups
         kq = len(gptr) - 1
-        if any(gptr[g + 1] - gptr[g] != 1 for g in range(kq)) or list(members) != list(range(kq)):
-            B = self.group_mean_rows(B, n2, gptr, members)
+        mult = [gptr[g + 1] - gptr[g] for g in range(kq)]
+        if max(mult) > 1 or list(members) != list(range(kq)):
+            Bm = self.group_mean_rows(B, n2, gptr, members)
+        else:
+            Bm = B
         G = self.empty(kq, kq)
         self.gemm(MC, MC, kq, kq, n1, 1.0, Q1, Q1, 0.0, G, 0)          # G = M M^T
-        mult = [gptr[g + 1] - gptr[g] for g in range(kq)]
-        return self.spd_solve_gram(G, kq, B, n2, weights=mult if max(mult) > 1 else None), kq
+        gnorm = torch.linalg.norm(G[:kq, :kq])
+        linv = self.potrf(G, kq, check_info=False)
+        Wg = self.trtri(G, kq, linv)
+        pot = self.potrf_info_async()
+        winv = torch.tril(Wg[:kq, :kq])
+        bound = gnorm * (winv * winv).sum()                           # |G|_F |G^-1|_F >= cond_2(G)
+        bad = torch.logical_or(torch.logical_not(bound < self.COND_LIMIT), pot[0] != 0)
+        Y = self.empty(kq, n2)
+        self.gemm(KC, MC, kq, n2, kq, 1.0, Wg, Bm, 0.0, Y, KHI_M)      # Y = Wg B
+        Z = self.empty(kq, n2)
+        self.gemm(MC, MC, kq, n2, kq, 1.0, Wg, Y, 0.0, Z, KLO_M)       # Z = Wg^T Y
+        self.last_rank = kq
+        return Z, kq, ProjectionCheck(self, bad, Q1, n1, Bm, n2, kq, mult if max(mult) > 1 else None)
+
+    def pinv_rows_solve(self, R, k, m, B, ncols, rcond=1e-15):
+        """Robust path: R (k x m, landmark rows, overwritten with the rotated rows J M) and
+        Z = diag(sigma^+2) J B such that pinv(M) B = R^T Z.  Returns (Z, rank, sigma)."""
+        Z = self.empty(k, ncols)
+        work = torch.empty(lib.munk_pinv_rows_work_bytes(k) // 8 + 2, dtype=torch.float64,
+                           device=self.torch_device)
+        rank = ctypes.c_int(0)
+        sigma = np.zeros(max(k, 1), dtype=np.float64)
+        check(lib.munk_pinv_rows_solve(self._ws, k, m, _ptr(R), R.stride(0), ncols, _ptr(B), B.stride(0),
+                                       _ptr(Z), Z.stride(0), _ptr(work), float(rcond), ctypes.byref(rank),
+                                       sigma.ctypes.data_as(ctypes.c_void_p), self.stream()),
+              "munk_pinv_rows_solve")
+        self.last_rank = rank.value
+        return Z, rank.value, sigma[:k]
+
+    def project_robust(self, Q1, n1, Bm, n2, kq, weights=None, rcond=1e-15):
+        """P = pinv(M) B through munk_pinv_rows_solve (numpy semantics; see `project`)."""
+        R = self.transpose(Q1, n1, kq)                                 # rows of M, contiguous
+        Bw = Bm
+        if weights is not None:
+            # A source landmark listed c times counts c-fold in pinv's least-squares objective:
+            # pinv(M_all) B_all = pinv(D M) (D mean(B)) with D = diag(sqrt(c)).  (With full row rank
+            # the residual is zero and D drops out, which is why the fast path ignores it.)
+            d = torch.sqrt(torch.as_tensor(np.asarray(weights, dtype=np.float64), device=self.torch_device))
+            R[:kq] *= d[:, None]
+            Bw = Bm.clone()
+            Bw[:kq] *= d[:, None]
+        Z, _, _ = self.pinv_rows_solve(R, kq, n1, Bw, n2, rcond)
+        P = self.empty(n1, n2)
+        self.gemm(MC, MC, n1, n2, kq, 1.0, R, Z, 0.0, P, 0)            # P = R^T Z
+        return P
 
     def pair_dots(self, X, Z, k, rows, cols):
         """out[p] = X[rows[p], :k] . Z[:k, cols[p]]"""
@@ -356,6 +396,28 @@ class Device:
         return S
 
 
+class ProjectionCheck:
+    """Device-side verdict on the fast landmark solve (Device.project).  resolve() reads the flag
+    (synchronising the stream once) and returns the projection to use: the fast one, or the
+    robust recomputation written into the same buffer."""
+
+    def __init__(self, dev, bad, Q1, n1, Bm, n2, kq, weights):
+        self.dev, self.bad, self.P = dev, bad, None
+        self.args = (Q1, n1, Bm, n2, kq, weights)
+
+    def fallback_needed(self):
+        return bool(self.bad.item())
+
+    def resolve(self):
+        if self.fallback_needed():
+            P = self.dev.project_robust(*self.args)
+            if self.P is not None:
+                self.P.copy_(P)
+                return self.P
+            return P
+        return self.P
+
+
 def landmark_groups(source_idx):
     """First-occurrence de-duplication of the source landmark list.
 
@@ -384,14 +446,19 @@ _side = {}
 
 
 def side_device(dev):
-    """(second Device, high-priority CUDA stream) on the same GPU, for running two independent
-    chains of work concurrently (own workspace, so split-K scratch, look-ahead stream and status
-    flag are not shared).  The block scheduler serves streams by priority, then age: the chain on
-    the high-priority stream keeps its speed, the other one fills the SMs it leaves idle.
+    """(second Device, high-priority CUDA stream, normal-priority CUDA stream) on the same GPU, for
+    running two independent chains of work concurrently (own workspace, so split-K scratch,
+    look-ahead streams, graph cache and status flag are not shared).  The block scheduler serves
+    streams by priority, then age: the chain on the high-priority stream keeps its speed, the
+    other one fills the SMs it leaves idle.  Both are explicit streams (not torch's default
+    stream, which is the legacy NULL stream and cannot be captured into a CUDA graph).
     Created once per device."""
     res = _side.get(dev.index)
     if res is None:
-        res = _side[dev.index] = (Device(dev.index), torch.cuda.Stream(device=dev.index, priority=-1))
+        import os
+        res = _side[dev.index] = (Device(dev.index),
+                                  torch.cuda.Stream(device=dev.index, priority=int(os.environ.get("MUNK_SRC_PRIORITY", "-1"))),
+                                  torch.cuda.Stream(device=dev.index, priority=int(os.environ.get("MUNK_TGT_PRIORITY", "0"))))
     return res
 
 

@@ -1,19 +1,25 @@
-"""Multi-GPU MUNK pipeline: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch).
+"""Multi-GPU MUNK pipeline: one process per GPU, NCCL over NVLink/NVSwitch.
 
 Process grid.  The factorisations use a 1 x P block-column-cyclic layout (block width 512) dealt
-in serpentine rounds (ranks 0..P-1, then P-1..0, ...; ColumnCyclic.owner).  With NVSwitch every rank sees every peer at full bandwidth, so
-the per-rank panel traffic of a P_r x P_c grid (the whole panel, n^2/2 doubles in total) is the
-same for any grid shape; 1 x P keeps each panel's factorisation on one GPU (no intra-panel
-exchange) and leaves every rank with the complete factor L, which is what the later stages want:
+in serpentine rounds (ranks 0..P-1, then P-1..0, ...; ColumnCyclic.owner).  The panel loop itself
+lives in the C library (csrc/dist.cu, entry points munk_dist_* / munk_comm_* of
+include/munk_b200.h): panel-major factor storage that is both working storage and broadcast
+buffer, ncclBroadcast straight from / into it on the library's own communicator, the critical
+chain on a high-priority stream, and the forward substitution fused into the loop.  This module
+owns what stays on the host: the ownership map, the staircase right-hand sides, the schedule of
+the stages, result sinks and gathers.
 
-  potrf   right-looking; the owner of panel j+1 applies panel j to it first (look-ahead), factors
-          it (diagonal block + panel solve, munk_potrf / munk_trsm_right) and broadcasts it
-          (ncclBroadcast, asynchronous) while all ranks apply panel j to the block columns they
-          own (DMMA syrk).  At the end every rank holds all of L and the leaf inverses.
+  potrf   right-looking, critical path first: per block column the owner runs LA_D -> F -> TS_N and
+          broadcasts [leaf inverses | diagonal + next block rows] (a few MB) on the chain stream,
+          then the rest of the panel on a second stream; every rank applies the panel to the block
+          columns it owns.  Only owned columns are assembled and updated (1/P of the matrix per rank).
   W, Q1   columns of W = L^-1 are independent given L: each rank solves L X = E for the identity
-          columns of its own blocks and (redundantly, k columns) for the landmark columns, in ONE
-          forward solve whose right-hand side is a staircase (munk_trsm_left with `stair`), so
-          only the non-zero part of every column is computed: n^3/(3P) flops per rank, no exchange.
+          columns of its own blocks and (redundantly, k columns) for the landmark columns; the
+          right-hand side is a staircase, so only the non-zero part of every column is computed
+          (n^3/(3P) flops per rank), and the substitution is FUSED into the panel loop: panel c is
+          applied to X the moment it arrives, in the SMs the latency-bound chain leaves idle.
+  D2 rows the target's k landmark columns ride its panel loop the same way; one backward
+          substitution (munk_dist_solve_backward) finishes A2^-1 E_Lt.
   C1, S   rank r owns the rows of C1 = W^T and of S = C1 C2hat^T that belong to its blocks
           (row-block sharding): S_r = X_r^T P with the same staircase on the k-range.
           P = C2hat^T is small work (2 n1 n2 k flops) and is formed on every rank from the
@@ -21,14 +27,19 @@ exchange) and leaves every rank with the complete factor L, which is what the la
   stats   separate_scores means: per-rank partial sums + one 4-scalar all-reduce.
   perms   permutation test: munk_b200/permtest.py (round-robin, one all-gather of 3 doubles each).
 
-The driver is written against a small `ops` object so that the schedule, the ownership map and the
-packing can be exercised on CPU tensors with gloo (tests/test_dist_cpu.py supplies a torch-CPU
-`ops`); the product always uses CudaOps (no CPU fallback: CudaOps needs a Device).
+The Python generator dist_potrf_steps (round 1's panel loop, written against a small `ops` object)
+is kept as the executable specification of the ownership / look-ahead order: tests/test_dist_cpu.py
+runs it on CPU tensors with gloo.  The product path does not use it.
 """
+import ctypes
+import os
+import threading
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from ._lib import check, lib
 from .device import KC, MC, TILE_LOWER, pad16, landmark_groups
 
 NB = 512
@@ -189,6 +200,139 @@ def dist_potrf_flag(ops, device, world, group=None):
     return int(flag.item())
 
 
+class DistComm:
+    """An NCCL communicator owned by the C library (munk_comm_*), one per concurrently running
+    factorisation.  Creation is collective: rank 0's unique id travels through torch.distributed."""
+
+    def __init__(self, dev, rank, world, group=None):
+        self.rank, self.world = rank, world
+        self._h = ctypes.c_void_p()
+        ident = torch.zeros(128, dtype=torch.uint8, device=dev.torch_device)
+        if world > 1:
+            if rank == 0:
+                buf = ctypes.create_string_buffer(128)
+                check(lib.munk_comm_unique_id(buf), "munk_comm_unique_id")
+                ident.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+            dist.broadcast(ident, src=_global_rank(group, 0), group=group)
+        raw = bytes(ident.cpu().numpy().tobytes())
+        with torch.cuda.device(dev.index):
+            check(lib.munk_comm_create(dev.index, rank, world, raw, ctypes.byref(self._h)), "munk_comm_create")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib.munk_comm_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+class DistFactor:
+    """One SPD matrix I + lam L factored over the ranks of a DistComm (munk_dist_*): panel-major
+    storage (about n^2 / 2 doubles per rank, allocated once and reused), assembly of the owned
+    block columns, the stepwise factorisation with an optional fused forward substitution, the
+    backward substitution and an unpack into an ordinary lower-triangular matrix (tests)."""
+
+    def __init__(self, dev, comm, n):
+        assert lib.munk_dist_block() == NB
+        self.dev, self.comm, self.n = dev, comm, int(n)
+        self.storage = torch.empty(lib.munk_dist_storage_elems(self.n), dtype=torch.float64,
+                                   device=dev.torch_device)
+        self._h = ctypes.c_void_p()
+        check(lib.munk_dist_create(dev._ws, comm._h if comm is not None else None, self.n,
+                                   ctypes.c_void_p(self.storage.data_ptr()), ctypes.byref(self._h)),
+              "munk_dist_create")
+        self._keep = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib.munk_dist_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def assemble(self, edges, lam):
+        dev = self.dev
+        u, v = dev.ints(edges[0]), dev.ints(edges[1])
+        w = d = None
+        if len(edges) == 4:
+            w, d = dev.doubles(edges[2]), dev.doubles(edges[3])
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        check(lib.munk_dist_assemble(self._h, int(u.numel()), ptr(u), ptr(v), ptr(w), ptr(d), float(lam),
+                                     dev.stream()), "munk_dist_assemble")
+
+    def set_rhs(self, X, ncols, stair):
+        self._keep = (X, stair)
+        check(lib.munk_dist_set_rhs(self._h, ctypes.c_void_p(X.data_ptr()) if X is not None else None,
+                                    X.stride(0) if X is not None else 0, int(ncols),
+                                    ctypes.c_void_p(stair.data_ptr()) if stair is not None else None),
+              "munk_dist_set_rhs")
+
+    def begin(self):
+        check(lib.munk_dist_potrf_begin(self._h, self.dev.stream()), "munk_dist_potrf_begin")
+
+    def step(self):
+        left = ctypes.c_int(0)
+        check(lib.munk_dist_potrf_step(self._h, ctypes.byref(left)), "munk_dist_potrf_step")
+        return left.value
+
+    def end(self):
+        check(lib.munk_dist_potrf_end(self._h), "munk_dist_potrf_end")
+
+    def factor(self):
+        self.begin()
+        self.end()
+
+    def solve_backward(self, X, ncols):
+        check(lib.munk_dist_solve_backward(self._h, ctypes.c_void_p(X.data_ptr()), X.stride(0), int(ncols),
+                                           self.dev.stream()), "munk_dist_solve_backward")
+
+    def unpack(self):
+        L = torch.zeros((self.n, pad16(self.n)), dtype=torch.float64, device=self.dev.torch_device)
+        check(lib.munk_dist_unpack(self._h, ctypes.c_void_p(L.data_ptr()), L.stride(0), self.dev.stream()),
+              "munk_dist_unpack")
+        return L
+
+
+def onehot_rhs(n, cols, device):
+    """(X, stair): X (n x pad128(len(cols))) with X[cols[l], l] = 1 and the first non-zero row of
+    each 128-column tile."""
+    cols = np.asarray(cols, dtype=np.int64)
+    width = max(128, (len(cols) + 127) // 128 * 128)
+    X = torch.zeros((n, width), dtype=torch.float64, device=device)
+    if len(cols):
+        X[torch.as_tensor(cols, device=device), torch.arange(len(cols), device=device)] = 1.0
+    stair = np.full(width // 128, n, dtype=np.int32)
+    for t in range(width // 128):
+        part = cols[128 * t:128 * (t + 1)]
+        if len(part):
+            stair[t] = int(part.min())
+    return X, torch.from_numpy(stair).to(device)
+
+
+_DIST = {}
+_THREADS = os.environ.get("MUNK_DIST_THREADS", "1") != "0"
+
+
+def _dist_resources(dev, n1, n2, rank, world, group):
+    """Per-process state of the distributed pass, created once per (device, sizes, group): second
+    workspace + stream for the target chain, one C-side NCCL communicator per chain, and the two
+    panel-major factor stores.  Collective on first call."""
+    key = (dev.index, n1, n2, world, id(group))
+    res = _DIST.get(key)
+    if res is None:
+        from .device import Device
+        dev2 = Device(dev.index)
+        comm1 = DistComm(dev, rank, world, group) if world > 1 else None
+        comm2 = DistComm(dev, rank, world, group) if world > 1 else None
+        res = _DIST[key] = dict(dev2=dev2, side=torch.cuda.Stream(device=dev.index), comm1=comm1, comm2=comm2,
+                                fac1=DistFactor(dev, comm1, n1), fac2=DistFactor(dev2, comm2, n2))
+    return res
+
+
 _SIDE = {}
 
 
@@ -342,49 +486,80 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
         members.extend(members_f[gptr_f[g]:gptr_f[g + 1]])
         gptr.append(len(members))
 
-    # 1. factors, replicated on every rank.  The target chain (assembly, Cholesky, the k-column
-    #    solve for D2[Lt,:]) is independent of the source chain and, like it, latency-bound in its
-    #    panel steps, so it runs concurrently: own stream, own workspace, own communicator.
+    # 1. Both factorisations, each with its forward substitution fused into the panel loop
+    #    (csrc/dist.cu).  Source: X = [my columns of W1 | landmark columns Q1] (staircase one-hot
+    #    right-hand side).  Target: the k landmark columns of the identity.  The chains are
+    #    independent and latency-bound in their block-column chain, so they run concurrently: own
+    #    stream, own workspace, own NCCL communicator, and - because every block column costs the
+    #    host ~100 launches - own host thread (the C calls release the GIL).
     main = torch.cuda.current_stream(dev.index)
-    dev2, side, group2 = _side_resources(dev, world, group)
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        A2 = dev2.assemble(n2, edges2[0], edges2[1], tgt_lam)
-        linv2 = dev2.new_linv(n2)
-        ops2 = CudaOps(dev2)
-    A1 = dev.assemble(n1, edges1[0], edges1[1], src_lam)
-    linv1 = dev.new_linv(n1)
-    # interleave the two panel loops step by step (one host thread feeds both streams)
-    src_steps = dist_potrf_steps(ops, A1, n1, linv1, rank, world, group)
-    tgt_steps = dist_potrf_steps(ops2, A2, n2, linv2, rank, world, group2, stream=side)
-    src_live = tgt_live = True
-    while src_live or tgt_live:
-        if src_live:
-            src_live = next(src_steps, "done") != "done"
-        if tgt_live:
-            tgt_live = next(tgt_steps, "done") != "done"
-    with torch.cuda.stream(side):
-        B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
-    mark("potrf_src")
-    # 2. my columns of W1 and the landmark columns Q1, one staircase solve
+    res = _dist_resources(dev, n1, n2, rank, world, group)
+    dev2, side, fac1, fac2 = res["dev2"], res["side"], res["fac1"], res["fac2"]
     cc = ColumnCyclic(n1, world)
     rows = cc.rows_of(rank)
+    side.wait_stream(main)
+
+    def target_chain():
+        with torch.cuda.device(dev.index), torch.cuda.stream(side):
+            t_ev[0].record()
+            fac2.assemble(edges2, tgt_lam)
+            X2, stair2 = onehot_rhs(n2, t_idx, dev.torch_device)
+            fac2.set_rhs(X2, X2.shape[1], stair2)
+            fac2.factor()
+            fac2.solve_backward(X2, X2.shape[1])               # X2 = A2^-1 E_Lt = D2[:, Lt]
+            res["B"] = dev2.transpose(X2, n2, len(t_idx))       # D2[Lt, :]  (k x n2)
+            res["flag2"] = dev2.potrf_info_async()
+            t_ev[1].record()
+
+    t_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    threaded = world > 1 and _THREADS
+    if threaded:
+        worker = threading.Thread(target=target_chain)
+        worker.start()
+    fac1.assemble(edges1, src_lam)
     X, stair, n_own_pad = staircase_rhs(n1, rows, uniq, dev.torch_device)
-    ncols = X.shape[1]
-    if ncols >= 128:
-        dev.trsm_left(A1, n1, linv1, X, ncols, transposed=False, stair=stair)
+    fac1.set_rhs(X, X.shape[1], stair)
+    if threaded:
+        fac1.factor()
+        worker.join()
+    else:
+        # one host thread: interleave the two panel loops block column by block column
+        with torch.cuda.stream(side):
+            t_ev[0].record()
+            fac2.assemble(edges2, tgt_lam)
+            X2, stair2 = onehot_rhs(n2, t_idx, dev.torch_device)
+            fac2.set_rhs(X2, X2.shape[1], stair2)
+            fac2.begin()
+        fac1.begin()
+        left1 = left2 = 1
+        while left1 or left2:
+            if left1:
+                left1 = fac1.step()
+            if left2:
+                with torch.cuda.stream(side):
+                    left2 = fac2.step()
+        fac1.end()
+        with torch.cuda.stream(side):
+            fac2.end()
+            fac2.solve_backward(X2, X2.shape[1])
+            res["B"] = dev2.transpose(X2, n2, len(t_idx))
+            res["flag2"] = dev2.potrf_info_async()
+            t_ev[1].record()
+    B, flag2 = res.pop("B"), res.pop("flag2")
+    mark("factor_solve_src")
     kq = len(uniq)
     Q1 = X[:, n_own_pad:]                                        # n1 x pad128(k'), view
+    mark("factor_extract_src")
 
-    mark("solve_src")
-    # 3. projection (replicated): join the target chain, check both factorisations
+    # 2. projection (replicated): join the target chain.  The factorisation flags and the verdict
+    #    on the fast landmark solve stay on the device (no host sync here: the host keeps
+    #    enqueuing) and are inspected once at the end of the step.
     main.wait_stream(side)
-    for t in (A2, linv2, B):
+    for t in (B, flag2):
         t.record_stream(main)
-    # the factorisation flags are parked in device ints (no host sync here: the host keeps
-    # enqueuing) and inspected once at the end of the step
-    flags = torch.cat([dev.potrf_info_async(), dev2.potrf_info_async()]).to(torch.int64)
-    P = dev.project(Q1, n1, B, n2, (gptr, members))
+    flag1 = dev.potrf_info_async()
+    P, verdict = dev.project(Q1, n1, B, n2, (gptr, members), defer=True)
+    flags = torch.stack([flag1[0].to(torch.int64), flag2[0].to(torch.int64), verdict.bad.to(torch.int64) * -1])
     if sink is not None:
         sink.push_C1(X, len(rows))
         sink.push_P(P)
@@ -406,15 +581,25 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
     C1 = X[:, :m_own].t() if m_own else X[:, :0].t()            # (m_own, n1) view of the solve
 
     mark("score")
-    bad = flags.max().reshape(1)
+    worst = torch.stack([flags[:2].max(), -flags[2]])
     if world > 1:
-        dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=group)
-    bad = int(bad.item())
-    if bad:
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=group)
+    worst = worst.cpu()
+    if int(worst[0]):
         from .device import NotPositiveDefinite
-        raise NotPositiveDefinite("matrix is not positive definite (pivot %d)" % (bad - 1))
+        raise NotPositiveDefinite("matrix is not positive definite (pivot %d)" % (int(worst[0]) - 1))
+    if int(worst[1]):
+        # rare: dependent landmark rows.  Every rank redoes the projection with the robust path
+        # (the verdict is the same everywhere: Q1 and B are replicated) and its score rows.
+        P = verdict.resolve()
+        if sink is not None:
+            sink.push_P(P)
+        if m_own:
+            dev.gemm_stair(MC, MC, m_own, n2, n1, 1.0, X, P, 0.0, S, 0, stair_m=stair, k0=0)
+            if sink is not None:
+                sink.push_S(S, 0, m_own)
     mark("flag_check")
-    out = dict(rows=rows, C1=C1, P=P, S=S[:m_own], n1=n1, n2=n2)
+    out = dict(rows=rows, C1=C1, P=P, S=S[:m_own], n1=n1, n2=n2, target_chain_events=t_ev)
     if homolog_idxs is not None:
         out["stats"] = dist_score_means(dev, S, rows, n1, n2, landmark_idxs, homolog_idxs, world, group)
     return out
@@ -463,12 +648,17 @@ def embed_and_score_distributed(dev, inputs, rank, world, src_lam=0.05, tgt_lam=
     source_X = dev.download(C1, n1, n1)
     target_X = dev.download(out["P"], n1, n2).T        # (n2, n1) transposed view, munk.py:109-110
     scores = dev.download(S, n1, n2)
-    # the reference's four timer keys (munk.py:161-164) mapped onto the distributed phases: both
-    # Cholesky chains run interleaved in the first, the W-column solves are the factorisation
-    runtimes = dict(source_regularized_laplacian_runtime=phase.get("potrf_src", 0.0),
-                    source_rkhs_factorization_runtime=phase.get("solve_src", 0.0),
-                    target_regularized_laplacian_runtime=0.0,
-                    embed_runtime=phase.get("embed", 0.0))
+    # The reference's four timer keys (munk.py:161-164), each the device time of its own phase
+    # (CUDA events on the phase's stream).  On N GPUs the source's Cholesky and the substitution
+    # that yields the factor C1 = L1^-T are ONE fused panel loop: its time is reported as the
+    # kernel phase, and the factorisation key is what is left to do afterwards (nothing: the loop
+    # ends with the columns of C1 in place), measured, not assumed.  The target chain runs
+    # concurrently, so the keys do not add up to the wall time.
+    t_ev = out["target_chain_events"]
+    runtimes = dict(source_regularized_laplacian_runtime=phase["factor_solve_src"],
+                    source_rkhs_factorization_runtime=phase["factor_extract_src"],
+                    target_regularized_laplacian_runtime=t_ev[0].elapsed_time(t_ev[1]) * 1e-3,
+                    embed_runtime=phase["embed"])
     return dict(source_X=source_X, target_X=target_X, scores=scores, source_nodes=inp["source_nodes"],
                 target_nodes=inp["target_nodes"], landmarks=inp["landmark_homs"], runtimes=runtimes,
                 score_runtime=phase.get("score", 0.0), wall=time.time() - t0)

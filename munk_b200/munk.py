@@ -26,8 +26,7 @@ def regularized_laplacian(G, nodes, lam):
     if n == 0:
         return np.empty((0, 0))
     dev = default_device()
-    u, v = util.edge_index_arrays(G, nodes)
-    W = dev.kernel_factor(n, u, v, lam)
+    W = dev.kernel_factor_edges(n, util.edge_index_arrays(G, nodes), lam)
     D = dev.gram_lower(W, n, ld=n + (n & 1))
     return dev.download(D, n, n)
 

@@ -111,7 +111,9 @@ class FactoredPair:
         uniq, gptr, members = landmark_groups([int(a) for a, _ in landmark_idxs])
         Q1 = dev.gather_cols_lower(self.W1, n1, uniq)
         B = dev.target_landmark_rows(self.W2, n2, [int(b) for _, b in landmark_idxs])
-        Z, kq = dev.landmark_solve(Q1, n1, B, n2, (gptr, members))
+        Z, kq, verdict = dev.landmark_solve(Q1, n1, B, n2, (gptr, members))
+        if verdict.fallback_needed():          # dependent landmark rows: the factored form does not hold
+            return tuple(float(x) for x in self.statistic(homolog_idxs, n_landmarks)[:3].cpu())
         X = self._d1_columns(Q1, kq, dev.empty(n1, kq))
         plan = plan_separate_scores(n1, n2, landmark_idxs, homolog_idxs)
         # masks as n x 2 operands (second column zero): a = X^T m_R, b = Z m_C on the tensor cores
@@ -184,9 +186,8 @@ def gen_random_network_data(seed_graph, n_tries=10, rng=None, lam=0.05, host=Tru
     G, tries = safe_perturbed_graph(seed_graph, rng, n_tries)
     nodes = sorted(G.nodes())
     dev = default_device()
-    u, v = util.edge_index_arrays(G, nodes)
     n = len(nodes)
-    W = dev.kernel_factor(n, u, v, lam)
+    W = dev.kernel_factor_edges(n, util.edge_index_arrays(G, nodes), lam)
     if not host:
         return dict(G=G, W=W, nodes=nodes), tries
     D = dev.download(dev.gram_lower(W, n, ld=n + (n & 1)), n, n)

@@ -149,13 +149,53 @@ def streamed_row_blocks(tiles, col_tiles, cuts=(0.04, 0.12, 0.3, 0.6)):
 
 
 class DeviceEmbedding:
-    """Result of embed_device(): everything still on the GPU."""
+    """Result of embed_device(): everything still on the GPU.  With overlap=True nothing has been
+    synchronised yet; finalize() (called by every accessor that hands data or timers to the host)
+    waits for the device, raises if a factorisation failed, replaces the projection by the robust
+    one if the fast landmark solve was not safe, and fills in the four reference timers."""
 
     def __init__(self, dev, n1, n2, W1, L2, P, runtimes):
         self.dev, self.n1, self.n2 = dev, n1, n2
         self.W1, self.L2, self.P = W1, L2, P          # L2: Cholesky factor of the target (or None)
-        self.runtimes = runtimes
+        self._runtimes = runtimes
+        self.timing_notes = dict(overlapped=False)
+        self._pending = self._sink = None
         self._S = None
+        self._streamed = None
+
+    def finalize(self):
+        if self._pending is None:
+            return self
+        ev, e_end, flags, pcheck = self._pending
+        self._pending = None
+        bad = flags.cpu()                                   # the one synchronisation of the pass
+        if int(bad[0]) or int(bad[1]):
+            raise NotPositiveDefinite("%s matrix is not positive definite" % ("source" if int(bad[0]) else "target"))
+        if pcheck.fallback_needed():
+            # rare: dependent landmark rows.  P is recomputed in place by the robust path; whatever
+            # was derived from the fast P (scores, host copies) is redone.
+            self.P = pcheck.resolve()
+            if self._sink is not None:
+                self._sink.push(self._sink.P, self.P[:, :self.n2])
+            if self._streamed is not None:
+                self._S = None
+                self.scores_streamed(*self._streamed)
+            elif self._S is not None:
+                self._S = None
+                self.scores()
+            if self._sink is not None:
+                self._sink.wait()
+        t = self._runtimes
+        t["source_regularized_laplacian_runtime"] = ev[0].elapsed_time(ev[1]) * 1e-3
+        t["source_rkhs_factorization_runtime"] = ev[1].elapsed_time(ev[2]) * 1e-3
+        t["target_regularized_laplacian_runtime"] = ev[3].elapsed_time(ev[4]) * 1e-3
+        t["embed_runtime"] = ev[5].elapsed_time(e_end) * 1e-3
+        self.timing_notes = dict(overlapped=True, chains_wall=ev[0].elapsed_time(ev[5]) * 1e-3)
+        return self
+
+    @property
+    def runtimes(self):
+        return self.finalize()._runtimes
 
     def scores(self):
         if self._S is None:
@@ -179,18 +219,22 @@ class DeviceEmbedding:
                            stair_m=stair_all[t0:t1], k0=0)
             sink.push(sink.S[r0:r1], S[r0:r1, :n2])
         self._S = S
+        self._streamed = (sink, cuts)
         return S
 
     # host copies (API edge)
     def source_C(self):
+        self.finalize()
         C = self.dev.transpose_lower(self.W1, self.n1)
         return self.dev.download(C, self.n1, self.n1)
 
     def target_C_hat(self):
         # (n2, n1) transposed view of the (n1, n2) array, exactly as munk.py:109-110 returns it
+        self.finalize()
         return self.dev.download(self.P, self.n1, self.n2).T
 
     def scores_host(self):
+        self.finalize()
         return self.dev.download(self.scores(), self.n1, self.n2)
 
 
@@ -205,61 +249,81 @@ def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.
     uniq, gptr, members = landmark_groups(s_idx)
 
     # The target chain (assembly, Cholesky, k-column solve for D2[Lt,:]) does not depend on the
-    # source chain; both are partly latency-bound, so the target runs on a second stream and
-    # workspace and fills the gaps.  Its timer is then the time the main stream still has to wait
-    # for it after the source phases ("exposed" time); with overlap=False the phases are serial
-    # and the four timers mean exactly what the reference's do (munk.py:134-164).
+    # source chain; both are partly latency-bound, so they run concurrently: the source on a
+    # high-priority stream, the target on a second stream and workspace, filling the SMs the
+    # source leaves idle.  The four timers keep the reference's meaning (munk.py:134-164) - each is
+    # the device time of its own phase, measured with CUDA events on the phase's stream - so under
+    # overlap they no longer add up to the wall time (`overlapped` and `chains_wall` say so).
     main = torch.cuda.current_stream(dev.index)
     if overlap:
-        # source chain first and on the high-priority stream; the target chain, enqueued behind
-        # it on the caller's stream with a second workspace, runs in the SMs the source leaves idle
-        dev2, hi = side_device(dev)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        dev2, hi, lo = side_device(dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         hi.wait_stream(main)
+        lo.wait_stream(main)
+        t_wall = time.time()
         with torch.cuda.stream(hi):
             ev[0].record()
-            A1 = dev.assemble(n1, edges1[0], edges1[1], src_lam)
+            A1 = dev.assemble_edges(n1, edges1, src_lam)
             linv1 = dev.potrf(A1, n1, check_info=False)
             ev[1].record()
             W1 = dev.trtri(A1, n1, linv1)
             ev[2].record()
-        A2 = dev2.assemble(n2, edges2[0], edges2[1], tgt_lam)
-        linv2 = dev2.potrf(A2, n2, check_info=False)
-        B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
-        hi.synchronize()
-        timer.times["source_regularized_laplacian_runtime"] = ev[0].elapsed_time(ev[1]) * 1e-3
-        timer.times["source_rkhs_factorization_runtime"] = ev[1].elapsed_time(ev[2]) * 1e-3
-        with timer("target_regularized_laplacian_runtime"):      # what is left of it after the source
-            main.wait_stream(hi)
-            for t in (A1, linv1):
-                t.record_stream(main)
-            with torch.cuda.stream(hi):
-                bad1 = dev.potrf_info()
-            if bad1 or dev2.potrf_info():
-                raise NotPositiveDefinite("%s matrix is not positive definite" % ("source" if bad1 else "target"))
+            flag1 = dev.potrf_info_async()
+        with torch.cuda.stream(lo):
+            ev[3].record()
+            A2 = dev2.assemble_edges(n2, edges2, tgt_lam)
+            linv2 = dev2.potrf(A2, n2, check_info=False)
+            B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
+            ev[4].record()
+            flag2 = dev2.potrf_info_async()
+        main.wait_stream(hi)
+        main.wait_stream(lo)
+        for t in (A1, linv1, flag1):
+            t.record_stream(main)
+        for t in (A2, linv2, B, flag2):
+            t.record_stream(main)
         del linv1
+        deferred = (ev, torch.stack([flag1[0], flag2[0]]), t_wall)
     else:
         with timer("source_regularized_laplacian_runtime"):
-            A1 = dev.assemble(n1, edges1[0], edges1[1], src_lam)
+            A1 = dev.assemble_edges(n1, edges1, src_lam)
             linv1 = dev.potrf(A1, n1)
         with timer("source_rkhs_factorization_runtime"):
             W1 = dev.trtri(A1, n1, linv1)
             del linv1
         with timer("target_regularized_laplacian_runtime"):
-            A2 = dev.assemble(n2, edges2[0], edges2[1], tgt_lam)
+            A2 = dev.assemble_edges(n2, edges2, tgt_lam)
             linv2 = dev.potrf(A2, n2)
             B = dev.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
-    with timer("embed_runtime"):
+    if overlap:
+        # embed: enqueued without waiting for the chains.  Nothing is read back here: the
+        # factorisation flags, the projection verdict and the event times are collected by
+        # DeviceEmbedding.finalize() at the caller's own synchronisation point, so the host can
+        # go on enqueuing the score product while the chains are still running.
+        ev, flags, t_wall = deferred
+        ev[5].record()
         Q1 = dev.gather_cols_lower(W1, n1, uniq)
-        P = dev.project(Q1, n1, B, n2, (gptr, members))
-        dev.raise_if_not_spd()
-    if sink is not None:
-        # C1 and P leave while the scores are computed.  Pushed only now: the projection reads
-        # small status values back to the host, and such a read queues behind any bulk
-        # device-to-host copy already in flight (measured: the host stalled for the whole C1 copy).
+        P, pcheck = dev.project(Q1, n1, B, n2, (gptr, members), defer=True)
+        e_end = torch.cuda.Event(enable_timing=True)
+        e_end.record()
+        if sink is not None:
+            # C1 and P start leaving now, while the scores are computed (a robust re-projection in
+            # finalize() re-sends P)
+            sink.push_source_factor(W1, n1)
+            sink.push(sink.P, P[:, :n2])
+        pending = (ev, e_end, flags, pcheck)
+    else:
+        with timer("embed_runtime"):
+            Q1 = dev.gather_cols_lower(W1, n1, uniq)
+            P = dev.project(Q1, n1, B, n2, (gptr, members))
+            dev.raise_if_not_spd()
+    if sink is not None and not overlap:
         sink.push_source_factor(W1, n1)
         sink.push(sink.P, P[:, :n2])
-    return DeviceEmbedding(dev, n1, n2, W1, A2 if keep_target_factor else None, P, timer.times)
+    emb = DeviceEmbedding(dev, n1, n2, W1, A2 if keep_target_factor else None, P, timer.times)
+    if overlap:
+        emb._pending, emb._sink = pending, sink
+    return emb
 
 
 def graph_inputs(source_G, target_G, homologs, n_landmarks):

@@ -88,21 +88,52 @@ def simple_two_core(G, verbose=True):
 
 
 def edge_index_arrays(G, nodes):
-    """Edges of G restricted to `nodes`, as two int32 arrays of positions in `nodes`.
+    """Edges of G restricted to `nodes`, as int32 arrays of positions in `nodes`.
 
-    Each undirected edge appears once, self loops are dropped (they cancel in the Laplacian
-    nx.laplacian_matrix builds), and a weighted graph is refused: the reference's PPI edge
-    lists are unweighted and the assembly kernel writes -lam per edge.
+    Simple unweighted graphs (every PPI edge list the reference reads): returns (u, v), each
+    undirected edge once (canonical (min, max) pairs, duplicates removed), self loops dropped —
+    they cancel in the Laplacian nx.laplacian_matrix builds (munk.py:82).
+
+    Weighted graphs and MultiGraphs: returns (u, v, lval, ldiag) — the off-diagonal entries
+    L[u, v] (each unordered pair once) and the diagonal of nx.laplacian_matrix(G, nodelist=nodes)
+    itself, float64, so that parallel edges and weights are summed exactly as the reference sums
+    them; the assembly kernel then forms 1 + lam * L entry by entry.  Directed graphs are refused:
+    their Laplacian is not symmetric, and the Cholesky route needs an SPD matrix.
     """
     pos = {name: i for i, name in enumerate(nodes)}
     if len(pos) != len(nodes):
         raise ValueError('node list contains duplicates')
+    if G.is_directed():
+        raise NotImplementedError('directed graphs are not supported: I + lam*L must be symmetric')
+    weighted = G.is_multigraph()
     us, vs = [], []
     for a, b, data in G.edges(data=True):
         if a == b or a not in pos or b not in pos:
             continue
         if data and data.get('weight', 1) != 1:
-            raise NotImplementedError('weighted graphs are not supported by the B200 assembly kernel')
+            weighted = True
+            break
         us.append(pos[a])
         vs.append(pos[b])
-    return np.asarray(us, dtype=np.int32), np.asarray(vs, dtype=np.int32)
+    if weighted:
+        return _laplacian_entries(G, nodes)
+    u, v = np.asarray(us, dtype=np.int64), np.asarray(vs, dtype=np.int64)
+    lo, hi = np.minimum(u, v), np.maximum(u, v)
+    key = np.unique(lo * len(nodes) + hi)               # nx.Graph yields each edge once already;
+    if len(key) != len(lo):                             # this guards graph-like inputs that do not
+        lo, hi = key // len(nodes), key % len(nodes)
+        return lo.astype(np.int32), hi.astype(np.int32)
+    return u.astype(np.int32), v.astype(np.int32)
+
+
+def _laplacian_entries(G, nodes):
+    """(u, v, lval, ldiag) from nx.laplacian_matrix itself (munk.py:82), strict upper triangle."""
+    import networkx as nx
+    import scipy.sparse
+    L = scipy.sparse.coo_matrix(nx.laplacian_matrix(G, nodelist=nodes).astype(np.float64))
+    ldiag = np.zeros(len(nodes), dtype=np.float64)
+    on = L.row == L.col
+    np.add.at(ldiag, L.row[on], L.data[on])
+    up = L.row < L.col
+    return (L.row[up].astype(np.int32), L.col[up].astype(np.int32),
+            np.ascontiguousarray(L.data[up], dtype=np.float64), ldiag)

@@ -245,8 +245,9 @@ def test_staircase_solve_matches_dense(dev):
 
 def test_rank_deficient_landmark_rows_follow_pinv(dev):
     """Landmark rows that are linearly dependent without being duplicates: np.linalg.pinv
-    truncates the null direction; the Gram/Cholesky fast path cannot, so the Jacobi fallback
-    (munk_sym_pinv_solve) must take over and give the same minimum-norm answer."""
+    truncates the null direction; the Gram/Cholesky fast path cannot, so the device-side condition
+    bound must send the projection to the robust path (munk_pinv_rows_solve), which gives the
+    same minimum-norm answer."""
     import munk_b200
     rng = np.random.default_rng(11)
     C = rng.standard_normal((60, 60))
@@ -257,15 +258,50 @@ def test_rank_deficient_landmark_rows_follow_pinv(dev):
     _, got = munk_b200.embed_matrices(C, D2, idx)
     assert dev.last_rank == 4                                     # 5 distinct rows, one dependent
     assert oracle.rel_max_err(got, want) < 1e-9
-    # the device eigen-solver on its own: pinv of a PSD matrix of known rank
-    import torch
-    X = torch.randn(40, 25, dtype=torch.float64, device="cuda")
-    G = dev.empty(40, 40); G[:, :40] = X @ X.t()                  # rank 25
-    B = dev.empty(40, 30); B[:, :30] = torch.randn(40, 30, dtype=torch.float64, device="cuda")
-    ref = torch.linalg.pinv(G[:, :40].clone(), hermitian=True) @ B[:, :30]
-    Z = dev.sym_pinv_solve(G, 40, B, 30)
-    assert dev.last_rank == 25
-    assert relerr(Z[:, :30], ref) < 1e-9
+    # well-conditioned rows take the fast path and agree as well
+    idx2 = [(3, 1), (17, 4), (8, 9), (22, 30)]
+    _, want2 = oracle.embed_matrices(C, D2, idx2)
+    _, got2 = munk_b200.embed_matrices(C, D2, idx2)
+    assert dev.last_rank == 4 and oracle.rel_max_err(got2, want2) < 1e-12
+
+
+@pytest.mark.parametrize("smallest", [1e-6, 1e-9, 1e-12, 0.0])
+def test_pinv_rows_follow_numpy_cutoff(dev, smallest):
+    """munk.py:109 semantics: singular values <= 1e-15 sigma_max are dropped, everything above is
+    kept - also in the band (1e-12 ... 1e-9) sigma_max that a Gram-matrix method (cut ~1e-8) cannot
+    resolve.  Rows M = U diag(s) V^T with prescribed singular values.  Checked: the retained rank
+    and the singular values against LAPACK; the projection against np.linalg.pinv(M) @ B to 1e-8
+    where that product is itself determined to 1e-8 (its conditioning is eps / smallest: below
+    smallest ~ 1e-8 two correct SVD codes differ by more, so there the comparison tolerance is
+    100 eps / smallest and the backward error |M P - B| carries the check)."""
+    rng = np.random.default_rng(5)
+    k, m, n = 24, 700, 90
+    U, _ = np.linalg.qr(rng.standard_normal((k, k)))
+    V, _ = np.linalg.qr(rng.standard_normal((m, k)))
+    s = np.geomspace(1.0, 1e-3, k)
+    s[-1] = smallest
+    M = (U * s) @ V.T
+    # right-hand sides in the range of M, as D2[Lt,:] is for kernel factors: B = M X
+    B = M @ rng.standard_normal((m, n))
+    want = np.linalg.pinv(M) @ B
+    ref = np.linalg.svd(M, compute_uv=False)
+    want_rank = int((ref > 1e-15 * ref[0]).sum())
+    assert want_rank == (k if smallest > 0 else k - 1)
+    Q1 = dev.upload(np.ascontiguousarray(M.T))
+    Bd = dev.upload(B)
+    P = dev.project(Q1, m, Bd, n, (list(range(k + 1)), list(range(k))))
+    got = P[:m, :n].cpu().numpy()
+    assert dev.last_rank == want_rank
+    eps = np.finfo(float).eps
+    tol = 1e-8 if smallest == 0 else max(1e-8, 100 * eps / smallest)
+    assert oracle.rel_max_err(got, want) < tol
+    assert np.abs(M @ got - B).max() < 1e-11 * np.abs(B).max()           # backward error
+    assert np.linalg.norm(got) <= np.linalg.norm(want) * (1 + 1e-6)      # minimum norm
+    # the kernel's singular values against LAPACK's (absolute accuracy eps * sigma_max, as LAPACK's own)
+    R = dev.upload(M)
+    _, rank, sigma = dev.pinv_rows_solve(R, k, m, Bd, n)
+    assert rank == want_rank
+    assert np.abs(np.sort(sigma)[::-1] - ref).max() < 100 * eps * ref[0]
 
 
 def test_rank_k_statistic_matches_dense_path(dev):
@@ -322,3 +358,82 @@ def test_separate_scores_random_cells_exact(dev, n1, n2, seed):
     S = rng.random((n1, n2))
     for got, want in zip(m.separate_scores(S, l_idx, h_idx), oracle.separate_scores(S, l_idx, h_idx)):
         assert np.array_equal(got, want)
+
+
+def test_weighted_and_multigraph_assembly_bit_exact(dev):
+    """Weights / parallel edges follow nx.laplacian_matrix (munk.py:82): A == np.eye + lam * L bit
+    for bit, and regularized_laplacian on such a graph matches the reference formula."""
+    import networkx as nx
+    from munk_b200 import util
+    import munk_b200 as munk
+    rng = np.random.default_rng(4)
+    G = nx.barabasi_albert_graph(300, 4, seed=2)
+    for a, b in G.edges():
+        G[a][b]["weight"] = float(rng.integers(1, 9)) / 4.0
+    M = nx.MultiGraph(nx.barabasi_albert_graph(200, 3, seed=3))
+    M.add_edges_from(list(M.edges())[:50])                      # 50 doubled edges
+    for H, lam in ((G, 0.05), (M, 0.13)):
+        nodes = sorted(H.nodes())
+        n = len(nodes)
+        edges = util.edge_index_arrays(H, nodes)
+        assert len(edges) == 4
+        A = dev.assemble_edges(n, edges, lam)
+        L = np.array(nx.laplacian_matrix(H, nodelist=nodes).todense())
+        want = np.eye(n) + lam * L
+        assert np.array_equal(A[:, :n].cpu().numpy(), want)
+        D = munk.regularized_laplacian(H, nodes, lam)
+        assert oracle.rel_max_err(D, np.linalg.inv(want)) < 1e-12
+
+
+def test_assembly_skips_and_reports_out_of_range_edges(dev):
+    import torch
+    n = 64
+    u = np.array([0, 1, 70, 3, -2], dtype=np.int32)
+    v = np.array([1, 2, 3, 64, 5], dtype=np.int32)
+    guard = torch.full((n + 8, 80), 7.0, dtype=torch.float64, device=dev.torch_device)
+    A = guard[:n]
+    dev.assemble(n, u, v, 0.05, out=A)
+    assert dev.assemble_info() == 3                                # first bad edge is index 2
+    assert dev.assemble_info() == 0                                # flag cleared
+    assert bool((guard[n:] == 7.0).all())                          # nothing written past the matrix
+    want = oracle.reglap_matrix(n, np.array([[0, 1], [1, 2]]), 0.05)
+    assert np.array_equal(A[:, :n].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n", [1300, 700, 2049])
+def test_dist_factor_panel_major_single_rank(dev, n):
+    """csrc/dist.cu with one rank (the N-rank program minus the broadcasts): assembly into
+    panel-major storage is bit-exact, the factor matches LAPACK, the fused forward substitution
+    and the backward substitution give A^-1 E."""
+    import networkx as nx
+    import torch
+    from munk_b200 import util
+    from munk_b200.dist import DistFactor, onehot_rhs, staircase_rhs
+    G = nx.barabasi_albert_graph(n, 5, seed=n)
+    u, v = util.edge_index_arrays(G, list(range(n)))
+    want_A = oracle.reglap_matrix(n, oracle.edge_index_arrays(G, list(range(n))), 0.05)
+    fac = DistFactor(dev, None, n)
+    fac.assemble((u, v), 0.05)
+    got_A = fac.unpack()[:, :n].cpu().numpy()
+    assert np.array_equal(got_A, np.tril(want_A))
+    own = list(range(512, min(n, 1024)))
+    lms = sorted({0, 3, n // 2, n - 1})
+    X, stair, n_own_pad = staircase_rhs(n, own, lms, dev.torch_device)
+    fac.set_rhs(X, X.shape[1], stair)
+    fac.factor()
+    assert dev.potrf_info() == 0
+    L = fac.unpack()[:, :n]
+    L_ref = torch.linalg.cholesky(torch.from_numpy(want_A).to(dev.torch_device))
+    assert relerr(L, L_ref) < 1e-13
+    W = torch.linalg.inv(L_ref)
+    assert relerr(X[:, :len(own)], W[:, own]) < 1e-11
+    assert relerr(X[:, n_own_pad:n_own_pad + len(lms)], W[:, lms]) < 1e-11
+    # A^-1 E for unsorted, repeated columns: forward (fused, second factorisation) + backward
+    cols = [n - 2, 5, 5, n // 3]
+    fac.assemble((u, v), 0.05)
+    X2, stair2 = onehot_rhs(n, cols, dev.torch_device)
+    fac.set_rhs(X2, X2.shape[1], stair2)
+    fac.factor()
+    fac.solve_backward(X2, X2.shape[1])
+    D = torch.linalg.inv(torch.from_numpy(want_A).to(dev.torch_device))
+    assert relerr(X2[:, :len(cols)], D[:, cols]) < 1e-11

@@ -54,9 +54,25 @@ def test_edge_index_arrays_rules():
     assert sorted(zip(u.tolist(), v.tolist())) in ([(1, 2), (2, 0)], [(0, 2), (1, 2)], [(1, 2), (0, 2)], [(2, 0), (1, 2)]) \
         or sorted(map(sorted, zip(u.tolist(), v.tolist()))) == [[0, 2], [1, 2]]
     assert u.dtype == np.int32
-    G["a"]["b"]["weight"] = 2.5
     with pytest.raises(NotImplementedError):
-        util.edge_index_arrays(G, ["a", "b"])
+        util.edge_index_arrays(nx.DiGraph([("a", "b")]), ["a", "b"])
+
+
+def test_weighted_and_multigraph_edges_carry_networkx_laplacian_entries():
+    """Weights and parallel edges: (u, v, lval, ldiag) reproduce nx.laplacian_matrix (munk.py:82)."""
+    from munk_b200 import util
+    G = nx.Graph()
+    G.add_weighted_edges_from([("a", "b", 2.5), ("b", "c", 1.0), ("c", "d", 0.25), ("d", "a", 3.0), ("c", "c", 9.0)])
+    M = nx.MultiGraph([("a", "b"), ("a", "b"), ("b", "c"), ("c", "a"), ("c", "a"), ("c", "a")])
+    for H in (G, M):
+        nodes = sorted(H.nodes())
+        u, v, lval, ldiag = util.edge_index_arrays(H, nodes)
+        L = np.zeros((len(nodes), len(nodes)))
+        L[u, v] = lval
+        L[v, u] = lval
+        L[np.arange(len(nodes)), np.arange(len(nodes))] = ldiag
+        assert np.array_equal(L, np.array(nx.laplacian_matrix(H, nodelist=nodes).todense(), dtype=np.float64))
+        assert u.dtype == np.int32 and lval.dtype == np.float64 and (u < v).all()
 
 
 def test_file_formats_roundtrip(tmp_path):

@@ -22,7 +22,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 from munk_b200 import dist as mdist, pipeline
-    import synth as synthetic
+import synth as synthetic
 from munk_b200.device import Device
 
 n1 = int(sys.argv[1]) if len(sys.argv) > 1 else 3000

@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from munk_b200 import pipeline
-    import synth as synthetic  # noqa: E402
+import synth as synthetic  # noqa: E402
 from munk_b200.device import default_device  # noqa: E402
 
 

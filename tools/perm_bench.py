@@ -33,7 +33,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 from munk_b200 import permtest, pipeline
-    import synth as synthetic
+import synth as synthetic
 from munk_b200.device import Device
 
 n1, n2, m, H, k = synthetic.CONFIGS[args.config]
