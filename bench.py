@@ -687,6 +687,8 @@ def run_gpu_dist(args, dev, rank, world, local):
             torch.cuda.current_stream().synchronize()
             for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
                 phase_ms.setdefault(name, []).append(a.elapsed_time(b))
+            te = out["target_chain_events"]
+            phase_ms.setdefault("target_chain_concurrent", []).append(te[0].elapsed_time(te[1]))
             step_ends.append((marks[0][1], marks[-1][1], time.perf_counter()))
         return out
 

@@ -169,6 +169,17 @@ int munk_download_upper(int n, const double* C, long ldc, double* host, long ldh
 int munk_download_block(int rows, int cols, const double* C, long ldc, double* host, long ldh,
                         void* stream);
 
+/*
+ * Device -> PAGEABLE host memory (a fresh numpy array the caller owns: the return values of
+ * munk.embed_networks / the score matrix of scripts/compute_embeddings.py:81).  Blocking.  `threads`
+ * worker threads (1..16), each with a pinned staging buffer and a stream of its own, move row chunks:
+ * DMA into the pinned buffer, then memcpy (and first touch) into `host`.  Work enqueued on `stream`
+ * before the call is waited for.  upper != 0 (square matrices): the source is upper triangular;
+ * columns left of each chunk's first row are zero-filled on the host instead of being moved.
+ */
+int munk_download_pageable(int device, long rows, long cols, const double* src, long lds, double* host,
+                           long ldh, int upper, int threads, void* stream);
+
 /* out[g][:] = mean of in[members[gptr[g] .. gptr[g+1])][:]; used to fold duplicated source
  * landmarks (np.linalg.pinv's minimum-norm least-squares answer, munk/munk/munk.py:109). */
 int munk_group_mean_rows(int ngroups, const int* gptr, const int* members, int ncols,

@@ -14,6 +14,7 @@ from .munk import (
     embed_networks,
     save_embeddings,
     scores,
+    release_device_cache,
 )
 
 __version__ = '0.1'

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libmunk_b200.so")
 SOURCES = ["api.cu", "dgemm.cu", "factor.cu", "leaf.cu", "assemble.cu", "scores.cu", "jacobi.cu",
-           "dist.cu", "microbench.cu"]
+           "dist.cu", "hostio.cu", "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     # dist.cu includes <nccl.h> for the types only; NCCL itself is dlopen'ed at run time (-ldl)
-    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", OUT] + srcs + ["-ldl"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", OUT] + srcs + ["-ldl", "-lpthread"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -98,6 +98,21 @@ class Device:
         torch.cuda.current_stream(self.index).synchronize()
         return host.numpy()
 
+    def download_fresh(self, buf, rows, cols, upper=False, threads=None):
+        """Device [:rows, :cols] -> a fresh (pageable) host ndarray through the multi-threaded
+        pinned staging path (munk_download_pageable): ~20-30 GB/s instead of the ~3 GB/s a plain
+        copy into untouched pageable memory reaches.  upper=True: `buf` is upper triangular (the
+        factor C1), the zero part is filled on the host instead of being copied.  Blocking."""
+        import os
+        out = np.empty((int(rows), int(cols)), dtype=np.float64)
+        if rows and cols:
+            if threads is None:
+                threads = max(2, min(12, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 8) - 2))
+            check(lib.munk_download_pageable(self.index, int(rows), int(cols), _ptr(buf), buf.stride(0),
+                                             out.ctypes.data_as(ctypes.c_void_p), int(cols), 1 if upper else 0,
+                                             int(threads), self.stream()), "munk_download_pageable")
+        return out
+
     # ---- kernels ----------------------------------------------------------------------------
     def gemm(self, a_layout, b_layout, M, N, K, alpha, A, B, beta, C, flags=0):
         check(lib.munk_dgemm(self._ws, a_layout, b_layout, M, N, K, alpha, _ptr(A), A.stride(0),

@@ -28,7 +28,7 @@ def regularized_laplacian(G, nodes, lam):
     dev = default_device()
     W = dev.kernel_factor_edges(n, util.edge_index_arrays(G, nodes), lam)
     D = dev.gram_lower(W, n, ld=n + (n & 1))
-    return dev.download(D, n, n)
+    return dev.download_fresh(D, n, n)
 
 
 def rkhs_factor(D):
@@ -49,7 +49,7 @@ def rkhs_factor(D):
     A = dev.upload(D)
     dev.potrf(A, n)
     C = dev.copy_lower(A, n, ld=n + (n & 1))
-    return dev.download(C, n, n)
+    return dev.download_fresh(C, n, n)
 
 
 def non_landmark_idxs(n, landmark_idxs):
@@ -79,9 +79,49 @@ def embed_matrices(source_C, target_D, landmark_idxs):
     return source_C, dev.download(P, d, n2).T
 
 
+# The last embedding embed_networks() produced stays on the device, so that the reference's next
+# step - np.dot(source_X, target_X.T) on the arrays it just returned
+# (scripts/compute_embeddings.py:72-81) - does not send 5.8 GB back up.  scores() uses it only for
+# the very arrays that embedding returned (object identity) and only if they are unchanged: a
+# fingerprint (every 4099th element of either array, taken when they were returned) is compared
+# first.  An in-place edit that touches none of the sampled elements is not noticed; copy the array
+# (or call release_device_cache()) before editing embeddings in place.
+_cache = None
+_FP_STRIDE = 4099
+
+
+def _fingerprint(arr):
+    flat = arr.reshape(-1) if arr.flags.c_contiguous else arr.T.reshape(-1)
+    return flat[::_FP_STRIDE].copy()
+
+
+def release_device_cache():
+    """Drops the device-resident copy of the last embedding (about (n1 + n2) n1 doubles of HBM)."""
+    global _cache
+    _cache = None
+
+
+def _cached_embedding(source_X, target_X):
+    c = _cache
+    if c is None:
+        return None
+    C1, P_host, emb, fp1, fp2 = c
+    base = target_X.base if isinstance(target_X, np.ndarray) else None
+    if source_X is not C1 or base is not P_host or target_X.shape != (P_host.shape[1], P_host.shape[0]):
+        return None
+    if not (np.array_equal(_fingerprint(C1), fp1) and np.array_equal(_fingerprint(P_host), fp2)):
+        return None
+    return emb
+
+
 def scores(source_X, target_X):
     """S = source_X . target_X^T on the GPU (scripts/compute_embeddings.py:81 np.dot,
-    permtest.py:55 `@`).  Host arrays in, host (n1, n2) array out."""
+    permtest.py:55 `@`).  Host arrays in, a fresh host (n1, n2) array out.  If the arguments are the
+    (unmodified) arrays embed_networks just returned, the product is formed from the factors still
+    on the device - only the triangle of C1 that is non-zero is contracted - and nothing is uploaded."""
+    emb = _cached_embedding(source_X, target_X)
+    if emb is not None:
+        return emb.dev.download_fresh(emb.scores(), emb.n1, emb.n2)
     X1 = np.asarray(source_X, dtype=np.float64)
     X2 = np.asarray(target_X, dtype=np.float64)
     n1, d = X1.shape
@@ -96,7 +136,7 @@ def scores(source_X, target_X):
         b_layout = KC
     S = dev.empty(n1, n2, ld=n2 + (n2 & 1))
     dev.gemm(KC, b_layout, n1, n2, d, 1.0, A, B, 0.0, S, 0)
-    return dev.download(S, n1, n2)
+    return dev.download_fresh(S, n1, n2)
 
 
 def embed_networks(source_G, target_G, homologs, n_landmarks,
@@ -105,20 +145,30 @@ def embed_networks(source_G, target_G, homologs, n_landmarks,
 
     ((source_C, source_nodes), (target_C_hat, target_nodes), landmark_homs, runtimes) or, with
     return_idxs, (..., landmark_idxs, homolog_idxs).  source_C = W^T is upper triangular (see
-    rkhs_factor); compare with the reference after orthogonal Procrustes alignment.
+    rkhs_factor); compare with the reference after orthogonal Procrustes alignment.  `runtimes`
+    has the reference's four keys, each the device time of its own phase (the source and target
+    chains run concurrently, so they do not add up to the wall time).
     """
+    global _cache
+    _cache = None                                   # free the previous embedding's HBM first
     inp = graph_inputs(source_G, target_G, homologs, n_landmarks)
     emb = embed_device(len(inp["source_nodes"]), inp["edges1"], len(inp["target_nodes"]),
-                       inp["edges2"], inp["landmark_idxs"], src_lam, tgt_lam)
-    source_C = emb.source_C()
-    target_C_hat = emb.target_C_hat()
+                       inp["edges2"], inp["landmark_idxs"], src_lam, tgt_lam, keep_target_factor=False)
+    emb.finalize()
+    dev, n1, n2 = emb.dev, emb.n1, emb.n2
+    C = dev.transpose_lower(emb.W1, n1)
+    source_C = dev.download_fresh(C, n1, n1, upper=True)
+    del C
+    P_host = dev.download_fresh(emb.P, n1, n2)
+    target_C_hat = P_host.T                         # (n2, n1) transposed view, exactly as munk.py:109-110
+    _cache = (source_C, P_host, emb, _fingerprint(source_C), _fingerprint(P_host))
     if return_idxs:
         s_pos, t_pos = inp["s_pos"], inp["t_pos"]
         homolog_idxs = [(s_pos[a], t_pos[b]) for a, b in homologs]
         return ((source_C, inp["source_nodes"]), (target_C_hat, inp["target_nodes"]),
                 inp["landmark_idxs"], homolog_idxs)
     return ((source_C, inp["source_nodes"]), (target_C_hat, inp["target_nodes"]),
-            inp["landmark_homs"], emb.runtimes)
+            inp["landmark_homs"], dict(emb.runtimes))
 
 
 def separate_scores(scores, landmark_pair_idxs, homolog_pair_idxs):

@@ -349,24 +349,57 @@ def index_inputs(source_nodes, edges1, target_nodes, edges2, homologs, n_landmar
 
 
 def embed_and_score(source_G, target_G, homologs, n_landmarks, src_lam=0.05, tgt_lam=0.05, dev=None,
-                    sink=None, inputs=None):
-    """Everything the CLI needs in one device-resident pass, results streamed to host memory
-    while the remaining stages run (pass a reusable pinned HostSink to avoid re-pinning).
+                    sink=None, inputs=None, on_embeddings=None):
+    """Everything the CLI needs in one device-resident pass (scripts/compute_embeddings.py:62-81).
     `inputs` = index_inputs(...) replaces the two graphs (fast ingestion path, no networkx).
 
-    Returns dict(source_X, target_X, scores, source_nodes, target_nodes, landmarks, runtimes).
+    Default (sink=None): fresh host arrays through the threaded staging path
+    (munk_download_pageable).  The two embeddings are brought down first and handed to
+    `on_embeddings(source_X, target_X)` - the CLI starts writing their pickles there - while the
+    score product runs on the GPU; the scores follow.  With a (reusable, pinned) HostSink the three
+    results stream into its buffers instead.
+
+    Returns dict(source_X, target_X, scores, source_nodes, target_nodes, landmarks, runtimes,
+    embed_wall) - embed_wall is what the reference's total_time measures (compute_embeddings.py:60-65):
+    embed_networks up to host-resident embeddings.
     """
     dev = dev or default_device()
     inp = inputs if inputs is not None else graph_inputs(source_G, target_G, homologs, n_landmarks)
     n1, n2 = len(inp["source_nodes"]), len(inp["target_nodes"])
-    sink = sink or HostSink(dev, n1, n2, pinned=False)
+    t_start = time.time()
     emb = embed_device(n1, inp["edges1"], n2, inp["edges2"], inp["landmark_idxs"], src_lam, tgt_lam,
                        dev=dev, keep_target_factor=False, sink=sink)
-    t0 = time.time()
-    emb.scores_streamed(sink)
-    sink.wait()
-    score_time = time.time() - t0
-    source_X, target_X, S = sink.arrays()
+    if sink is not None:
+        t0 = time.time()
+        emb.scores_streamed(sink)
+        sink.wait()
+        runtimes = dict(emb.runtimes)
+        score_time = time.time() - t0
+        source_X, target_X, S = sink.arrays()
+        embed_wall = time.time() - t_start
+    else:
+        emb.finalize()
+        # transpose first, then the score product: a kernel on another stream gets no SM while a
+        # long-tile DMMA launch occupies them all, a DMA does - so only copies overlap the scores
+        main = torch.cuda.current_stream(dev.index)
+        C = dev.transpose_lower(emb.W1, n1)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        Sdev = emb.scores()                                  # enqueued; runs while the embeddings leave
+        copy = torch.cuda.Stream(device=dev.index)
+        copy.wait_event(ready)                               # C and P are final; do not wait for S
+        with torch.cuda.stream(copy):
+            source_X = dev.download_fresh(C, n1, n1, upper=True)
+            target_X = dev.download_fresh(emb.P, n1, n2).T   # (n2, n1) view, munk.py:109-110
+        del C
+        embed_wall = time.time() - t_start
+        if on_embeddings is not None:
+            on_embeddings(source_X, target_X)
+        t0 = time.time()
+        S = dev.download_fresh(Sdev, n1, n2)
+        score_time = time.time() - t0
+        runtimes = dict(emb.runtimes)
     return dict(source_X=source_X, target_X=target_X, scores=S,
                 source_nodes=inp["source_nodes"], target_nodes=inp["target_nodes"],
-                landmarks=inp["landmark_homs"], runtimes=dict(emb.runtimes), score_runtime=score_time)
+                landmarks=inp["landmark_homs"], runtimes=runtimes, score_runtime=score_time,
+                embed_wall=embed_wall, timing_notes=emb.timing_notes)

@@ -6,8 +6,8 @@ files and schemas).  Graph ingestion (parse, largest component, self loops, 2-co
 map) runs on arrays (munk_b200.ingest, bit-exact with the reference's networkx path; pass
 --networkx_ingest to use networkx itself); the numeric work (both regularized-Laplacian kernels,
 the source RKHS factor, the landmark projection and the n1 x n2 score product) runs in one
-device-resident pass (munk_b200.pipeline.embed_and_score); the three result matrices stream back
-to the host while later stages are still computing.  Launched under torchrun
+device-resident pass (munk_b200.pipeline.embed_and_score); the embeddings come down and their
+pickles are written by worker threads while the score product is still running.  Launched under torchrun
 (`python -m torch.distributed.run --nproc-per-node N scripts/compute_embeddings.py ...`) the same
 pass is sharded over N GPUs and rank 0 writes the files.
 """
@@ -91,32 +91,45 @@ def run(args):
     log.info('Computing MUNK embeddings with %d landmarks', args.n_landmarks)
     inputs = pipeline.index_inputs(source_nodes, source_edges, target_nodes, target_edges, homologs,
                                    args.n_landmarks)
+    # The three pickles are ~8 GB at 20k/16k nodes; written one after the other they take as long as
+    # the whole compute stage.  They are written by worker threads (file writes release the GIL),
+    # the two embeddings while the score product is still running on the GPU.
+    from concurrent.futures import ThreadPoolExecutor
+    writers = ThreadPoolExecutor(max_workers=3)
+    pending = []
+
+    def save_both(source_X, target_X):
+        landmarks = inputs['landmark_homs']
+        log.info('Saving source species embeddings to %s', args.source_output_file)
+        pending.append(writers.submit(munk.save_embeddings, source_X, source_nodes, [a for a, _ in landmarks],
+                                      args.source_output_file))
+        log.info('Saving target species embeddings to %s', args.target_output_file)
+        pending.append(writers.submit(munk.save_embeddings, target_X, target_nodes, [b for _, b in landmarks],
+                                      args.target_output_file))
+
     started = time.time()
     if world > 1:
         res = mdist.embed_and_score_distributed(Device(local), inputs, rank, world,
                                                 src_lam=args.src_lam, tgt_lam=args.tgt_lam)
+        total_time = time.time() - started
+        if res is not None:
+            save_both(res['source_X'], res['target_X'])
     else:
         res = pipeline.embed_and_score(None, None, homologs, args.n_landmarks, src_lam=args.src_lam,
-                                       tgt_lam=args.tgt_lam, inputs=inputs)
-    total_time = time.time() - started
+                                       tgt_lam=args.tgt_lam, inputs=inputs, on_embeddings=save_both)
+        total_time = res['embed_wall']      # embed_networks up to host-resident embeddings (:60-65)
     if res is None:                 # ranks > 0 of a torchrun launch: rank 0 writes the files
         tdist.barrier()
         tdist.destroy_process_group()
         return
     landmarks = res['landmarks']
-
-    log.info('Saving source species embeddings to %s', args.source_output_file)
-    munk.save_embeddings(res['source_X'], res['source_nodes'], [a for a, _ in landmarks],
-                         args.source_output_file)
-    log.info('Saving target species embeddings to %s', args.target_output_file)
-    munk.save_embeddings(res['target_X'], res['target_nodes'], [b for _, b in landmarks],
-                         args.target_output_file)
     log.info('Source data shape {}'.format(res['source_X'].shape))
     log.info('Target data shape {}'.format(res['target_X'].shape))
 
     log.info('Saving MUNK similarity scores to %s', args.sim_scores_output_file)
-    joblib.dump(dict(X=res['scores'], A_nodes=res['source_nodes'], B_nodes=res['target_nodes'],
-                     landmarks=landmarks, homologs=homologs), args.sim_scores_output_file)
+    pending.append(writers.submit(joblib.dump, dict(X=res['scores'], A_nodes=res['source_nodes'],
+                                                    B_nodes=res['target_nodes'], landmarks=landmarks,
+                                                    homologs=homologs), args.sim_scores_output_file))
 
     log.info('Saving landmark list to %s', args.landmarks_output_file)
     with open(args.landmarks_output_file, 'w') as out:
@@ -126,6 +139,9 @@ def run(args):
     with open(args.runtimes_file, 'w') as out:
         json.dump(dict(n_source_nodes=len(source_nodes), n_target_nodes=len(target_nodes),
                        runtimes=res['runtimes'], total_time=total_time), out, indent=2)
+    for job in pending:
+        job.result()
+    writers.shutdown()
     log.info('MUNK embedding complete!')
     if world > 1:
         tdist.barrier()
