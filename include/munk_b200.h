@@ -85,6 +85,13 @@ int munk_assemble_reglap_entries(munk_workspace_t* ws, int n, int nnz, const int
  */
 int munk_potrf(munk_workspace_t* ws, int n, double* A, long ld, double* linv, void* stream);
 
+/* munk_potrf of two independent matrices (two workspaces on one device), e.g. the source and the
+ * target Laplacian of munk/munk/munk.py:135,145: the block columns of both are interleaved on one
+ * trailing-update stream, so that each factorisation's latency-bound diagonal-block chain hides
+ * behind the other's tensor-core work.  Flags and leaf inverses as for two munk_potrf calls. */
+int munk_potrf_pair(munk_workspace_t* wa, int na, double* A, long lda, double* linva, munk_workspace_t* wb,
+                    int nb, double* B, long ldb, double* linvb, void* stream);
+
 /* Synchronises `stream`; *info_host = 0 if every pivot so far was positive, else 1 + index of
  * the first bad column; the device flag is cleared. */
 int munk_potrf_info(munk_workspace_t* ws, int* info_host, void* stream);

@@ -27,6 +27,8 @@ SIGNATURES = {
     "munk_assemble_reglap_entries": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_double, c_void_p, c_long, c_void_p]),
     "munk_potrf": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p]),
+    "munk_potrf_pair": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p, c_int, c_void_p, c_long,
+                                c_void_p, c_void_p]),
     "munk_potrf_info": (c_int, [c_void_p, _P(c_int), c_void_p]),
     "munk_potrf_info_async": (c_int, [c_void_p, c_void_p, c_void_p]),
     "munk_trtri": (c_int, [c_void_p, c_int, c_void_p, c_long, c_void_p, c_void_p]),

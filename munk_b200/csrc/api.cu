@@ -123,6 +123,21 @@ int munk_potrf(munk_workspace_t* ws, int n, double* A, long ld, double* linv, vo
   return potrf_lower(ws, n, A, ld, linv, S(stream));
 }
 
+int munk_potrf_pair(munk_workspace_t* wa, int na, double* A, long lda, double* linva, munk_workspace_t* wb,
+                    int nb, double* B, long ldb, double* linvb, void* stream) {
+  if (!wa || !wb) return -1;
+  if (wa->device != wb->device) return -6;
+  DeviceGuard guard(wa->device);
+  if (na < 0) return -2;
+  if (nb < 0) return -7;
+  if (lda < na || (lda & 1)) return -4;
+  if (ldb < nb || (ldb & 1)) return -9;
+  if ((na > 0 && (!A || !linva)) || (nb > 0 && (!B || !linvb))) return -3;
+  if (na == 0) return potrf_lower(wb, nb, B, ldb, linvb, S(stream));
+  if (nb == 0) return potrf_lower(wa, na, A, lda, linva, S(stream));
+  return potrf_pair_lower(wa, na, A, lda, linva, wb, nb, B, ldb, linvb, S(stream));
+}
+
 int munk_potrf_info(munk_workspace_t* ws, int* info_host, void* stream) {
   if (!ws || !info_host) return -1;
   DeviceGuard guard(ws->device);

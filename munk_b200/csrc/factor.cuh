@@ -15,6 +15,11 @@ size_t linv_bytes_for(int n);
 // pivot was not positive.  Blocks above the diagonal keep whatever they held.
 int potrf_lower(Workspace* ws, int n, double* A, long ld, double* linv, cudaStream_t stream);
 
+// Two independent factorisations (two workspaces) with their block columns interleaved on one
+// trailing-update stream; results and flags as two potrf_lower calls.
+int potrf_pair_lower(Workspace* wa, int na, double* A, long lda, double* linva, Workspace* wb, int nb,
+                     double* B, long ldb, double* linvb, cudaStream_t stream);
+
 // In-place inverse of the lower-triangular factor produced by potrf_lower (same linv).
 int trtri_lower(Workspace* ws, int n, double* L, long ld, double* linv, cudaStream_t stream);
 

@@ -29,6 +29,7 @@ struct Workspace {
   // enqueue the independent target chain at once.
   struct GraphEntry {
     int op, n; const void* a; long ld; const void* linv;
+    int n2; const void* a2; long ld2; const void* linv2;      // second matrix of a paired factorisation
     cudaGraphExec_t exec;       // nullptr: seen once, not captured yet
     long launches; double flops;
     unsigned long stamp;

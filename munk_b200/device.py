@@ -165,6 +165,12 @@ class Device:
             self.raise_if_not_spd()
         return linv
 
+    def potrf_pair(self, A, n, linv, other, B, nb, linvb):
+        """In-place Cholesky of A (this workspace) and B (`other`'s workspace) with their block
+        columns interleaved on the current stream (munk_potrf_pair); flags are checked separately."""
+        check(lib.munk_potrf_pair(self._ws, n, _ptr(A), A.stride(0), _ptr(linv), other._ws, nb, _ptr(B),
+                                  B.stride(0), _ptr(linvb), self.stream()), "munk_potrf_pair")
+
     def potrf_info(self):
         info = ctypes.c_int(0)
         check(lib.munk_potrf_info(self._ws, ctypes.byref(info), self.stream()), "munk_potrf_info")

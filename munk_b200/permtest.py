@@ -77,8 +77,8 @@ class FactoredPair:
 
     def __init__(self, dev, n1, edges1, n2, edges2, lam=0.05):
         self.dev, self.n1, self.n2 = dev, n1, n2
-        self.W1 = dev.kernel_factor(n1, edges1[0], edges1[1], lam)
-        self.W2 = dev.kernel_factor(n2, edges2[0], edges2[1], lam)
+        self.W1 = dev.kernel_factor_edges(n1, edges1, lam)
+        self.W2 = dev.kernel_factor_edges(n2, edges2, lam)
         self._S = None
 
     def statistic(self, homolog_idxs, n_landmarks):
@@ -275,4 +275,38 @@ def run_permutation_test(source_G, target_G, homologs, n_landmarks, n_permutatio
     return dict(pval=pval, effect_size=float(effect_size(real[2], diffs)), n_permutations=n_obs,
                 n_less_than=n_less, errs=int((~ok).sum()),
                 real=dict(mean_diff=float(real[2]), non_hom_mean=float(real[1]), hom_mean=float(real[0])),
+                random=dict(mean_diffs=table[ok, 0], non_hom_means=table[ok, 1], hom_means=table[ok, 2]))
+
+
+def run_permutation_test_from_files(source_G, target_G, homologs, n_landmarks, source_data_files,
+                                    target_data_files, lam=0.05, rank=0, world=1):
+    """The reference's own mode (permtest.py:111-187): permutation p is the pickled pair
+    source_data_files[p] = dict(C, nodes), target_data_files[p] = dict(D, nodes) written by
+    gen_random_network.py; the unit is difference_in_means_from_files (permtest.py:82-99: any
+    exception is printed and counted).  The file pairs are dealt round-robin to the ranks."""
+    import joblib
+    from .munk import regularized_laplacian, rkhs_factor
+    dev = default_device()
+    source_nodes, target_nodes = sorted(source_G.nodes()), sorted(target_G.nodes())
+    source_data = dict(C=rkhs_factor(regularized_laplacian(source_G, source_nodes, lam)), nodes=source_nodes)
+    target_data = dict(D=regularized_laplacian(target_G, target_nodes, lam), nodes=target_nodes)
+    real_diff, other_mean, hom_mean = difference_in_means(source_data, target_data, homologs, n_landmarks,
+                                                          source_nodes, target_nodes)
+    del source_data, target_data
+    n_permutations = len(source_data_files)
+    local = {}
+    for p in shard(n_permutations, rank, world):
+        try:
+            local[p] = difference_in_means(joblib.load(source_data_files[p]), joblib.load(target_data_files[p]),
+                                           homologs, n_landmarks, source_nodes, target_nodes)
+        except Exception:
+            print('ERROR with {}, {}'.format(source_data_files[p], target_data_files[p]))
+            local[p] = None
+    table = gather_results(local, n_permutations, rank, world, device=dev.torch_device)
+    ok = ~np.isnan(table[:, 0])
+    diffs = table[ok, 0]
+    pval, n_less, n_obs = one_tail_pval(real_diff, diffs)
+    return dict(pval=pval, effect_size=float(effect_size(real_diff, diffs)), n_permutations=n_obs,
+                n_less_than=n_less, errs=int((~ok).sum()),
+                real=dict(mean_diff=float(real_diff), non_hom_mean=float(other_mean), hom_mean=float(hom_mean)),
                 random=dict(mean_diffs=table[ok, 0], non_hom_means=table[ok, 1], hom_means=table[ok, 2]))

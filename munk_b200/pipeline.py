@@ -16,6 +16,7 @@ from . import util
 from .device import MC, NotPositiveDefinite, default_device, landmark_groups, side_device
 
 B200_SMS = 148
+_PAIR = __import__("os").environ.get("MUNK_PAIR", "1") != "0"
 
 
 class PhaseTimer:
@@ -261,21 +262,49 @@ def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.
         hi.wait_stream(main)
         lo.wait_stream(main)
         t_wall = time.time()
-        with torch.cuda.stream(hi):
-            ev[0].record()
-            A1 = dev.assemble_edges(n1, edges1, src_lam)
-            linv1 = dev.potrf(A1, n1, check_info=False)
-            ev[1].record()
-            W1 = dev.trtri(A1, n1, linv1)
-            ev[2].record()
-            flag1 = dev.potrf_info_async()
-        with torch.cuda.stream(lo):
-            ev[3].record()
-            A2 = dev2.assemble_edges(n2, edges2, tgt_lam)
-            linv2 = dev2.potrf(A2, n2, check_info=False)
-            B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
-            ev[4].record()
-            flag2 = dev2.potrf_info_async()
+        if _PAIR:
+            # the two Cholesky factorisations as one interleaved schedule (munk_potrf_pair): each
+            # one's latency-bound diagonal-block chain hides behind the other's trailing updates.
+            # Then the source's triangular inverse and the target's landmark solves side by side.
+            with torch.cuda.stream(lo):
+                ev[3].record()
+                A2 = dev2.assemble_edges(n2, edges2, tgt_lam)
+                linv2 = dev2.new_linv(n2)
+                a2_ready = torch.cuda.Event()
+                a2_ready.record()
+            with torch.cuda.stream(hi):
+                ev[0].record()
+                A1 = dev.assemble_edges(n1, edges1, src_lam)
+                linv1 = dev.new_linv(n1)
+                hi.wait_event(a2_ready)
+                dev.potrf_pair(A1, n1, linv1, dev2, A2, n2, linv2)
+                for t in (A2, linv2):
+                    t.record_stream(hi)
+                ev[1].record()
+                W1 = dev.trtri(A1, n1, linv1)
+                ev[2].record()
+                flag1 = dev.potrf_info_async()
+            with torch.cuda.stream(lo):
+                lo.wait_event(ev[1])
+                B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
+                ev[4].record()
+                flag2 = dev2.potrf_info_async()
+        else:
+            with torch.cuda.stream(hi):
+                ev[0].record()
+                A1 = dev.assemble_edges(n1, edges1, src_lam)
+                linv1 = dev.potrf(A1, n1, check_info=False)
+                ev[1].record()
+                W1 = dev.trtri(A1, n1, linv1)
+                ev[2].record()
+                flag1 = dev.potrf_info_async()
+            with torch.cuda.stream(lo):
+                ev[3].record()
+                A2 = dev2.assemble_edges(n2, edges2, tgt_lam)
+                linv2 = dev2.potrf(A2, n2, check_info=False)
+                B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
+                ev[4].record()
+                flag2 = dev2.potrf_info_async()
         main.wait_stream(hi)
         main.wait_stream(lo)
         for t in (A1, linv1, flag1):
