@@ -454,11 +454,14 @@ def run_gpu(args):
                 side.wait_event(a2_ready)
                 dev.potrf_pair(A1, n1, linv1, dev2, A2, n2, linv2)
                 h2 = ev(); h2.record()
+            # the dense triangular inverse on the normal-priority stream, the latency-bound landmark
+            # solves on the high-priority one: their small kernels slot in at tile boundaries
+            with torch.cuda.stream(tgt_stream):
+                tgt_stream.wait_event(h2)
                 dev.trtri(A1, n1, linv1)
                 h3 = ev(); h3.record()
-            with torch.cuda.stream(tgt_stream):
+            with torch.cuda.stream(side):
                 s0 = s1 = h2
-                tgt_stream.wait_event(h2)
                 B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, tgt_idx)
                 s2 = ev(); s2.record()
         else:

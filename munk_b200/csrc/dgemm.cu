@@ -466,7 +466,8 @@ int gemm_launch(Workspace* ws, const GemmDesc& g, cudaStream_t stream, int scrat
   // of the recursive factorisations are latency-bound unless their k-range is spread out.
   // Each split keeps at least 2 k-iterations; partials are reduced in a fixed order.
   int nsplit = 1;
-  if (ws && active > 0 && active <= 111 && max_it >= 4 && !(g.flags & GF_SYM_MIRROR)) {
+  static const int split_min_it = [] { const char* e = getenv("MUNK_SPLITK_MIN_IT"); return e ? std::max(2, atoi(e)) : 4; }();
+  if (ws && active > 0 && active <= 111 && max_it >= split_min_it && !(g.flags & GF_SYM_MIRROR)) {
     nsplit = (int)std::min<long>((148 + active - 1) / active, max_it / 2);
     nsplit = std::max(1, std::min(nsplit, 74));
   }

@@ -32,6 +32,7 @@
 #include "dgemm.cuh"
 #include "factor_internal.cuh"
 #include "kernels.cuh"
+#include "leaf.cuh"
 #include "workspace.cuh"
 
 #include <dlfcn.h>
@@ -182,6 +183,16 @@ struct munk_dist {
   cudaEvent_t solve_done = nullptr;
   int next = 0;                           // next block column of the running factorisation
   bool running = false;
+  // MUNK_TRACE_DIST=1: device timeline of the chain / panel streams (diagnostics only)
+  bool trace = false;
+  std::vector<cudaEvent_t> tr;
+  void tick(cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tr.push_back(e);
+  }
 
   int w(int c) const { return start[c + 1] - start[c]; }
   int s(int c) const { return start[std::min(c, nblk)]; }
@@ -248,20 +259,35 @@ int dist_step(munk_dist* h, int c) {
   };
   auto ts = [&](cudaStream_t st, int scratch, int r0, int r1, int col) -> int {
     if (r1 <= r0) return MUNK_OK;
+    static const int strip_rows = env_int("MUNK_STRIP_ROWS", 1024);
+    if (r1 - r0 <= strip_rows) {            // the chain's TS_N: one strip-solve launch
+      MUNK_TRY(launch_trsm_strip(h->rows(col, r0), h->ldp[col], r1 - r0, h->rows(col, h->s(col)), h->ldp[col],
+                                 h->w(col), h->linv(col), st));
+      ws->launches++;
+      ws->flops += (double)(r1 - r0) * h->w(col) * h->w(col);
+      return MUNK_OK;
+    }
     Rec r = rec(st, scratch, col);
     return trsm_rec(r, h->rows(col, r0), h->ldp[col], r1 - r0, h->rows(col, h->s(col)), h->ldp[col], h->w(col), 0);
   };
 
   // ---- chain stream
+  h->tick(side);                                                     // 0: chain stream reaches column c
   if (h->own(c)) {
     if (c >= 2) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, upd_ev[c - 2], 0));
     if (c >= 1) MUNK_TRY(la(side, 1, h->s(c), h->s(c + 1), c));
+    h->tick(side);                                                   // 1: LA_D done
     Rec r = rec(side, 1, c);
     MUNK_TRY(potrf_rec(r, h->rows(c, h->s(c)), h->ldp[c], h->w(c), 0));
     MUNK_CUDA_TRY(cudaEventRecord(diag_ev[c], side));
+    h->tick(side);                                                   // 2: F done
     if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, lan_ev[c], 0));
     MUNK_TRY(ts(side, 1, h->s(c + 1), h->s(c + 2), c));
+  } else {
+    h->tick(side);
+    h->tick(side);
   }
+  h->tick(side);                                                     // 3: TS_N done (owner) / nothing
   if (multi) {
     // piece A(c): leaf inverses + rows D(c) and N(c), contiguous in the panel buffer
     const size_t count = (size_t)h->leaf_elems(c) + (size_t)(h->s(c + 2) - h->s(c)) * h->ldp[c];
@@ -269,6 +295,7 @@ int dist_step(munk_dist* h, int c) {
                                    h->comm->comm, side));
   }
   MUNK_CUDA_TRY(cudaEventRecord(top_ev[c], side));
+  h->tick(side);                                                     // 4: piece A here
   // ---- panel stream
   if (h->own(c)) {
     MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, diag_ev[c], 0));
@@ -281,6 +308,7 @@ int dist_step(munk_dist* h, int c) {
     MUNK_NCCL_TRY(nccl().Broadcast(p, p, count, ncclDouble, owner_of(c, h->world), h->comm->comm, side2));
   }
   MUNK_CUDA_TRY(cudaEventRecord(panel_ev[c], side2));
+  h->tick(side2);                                                    // 5: piece B here
   if (h->own(c + 1)) {
     if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, upd_ev[c - 1], 0));
     MUNK_TRY(la(side2, 2, h->s(c + 2), h->s(c + 3), c + 1));
@@ -506,6 +534,8 @@ int munk_dist_potrf_begin(munk_dist_t* h, void* stream_) {
   MUNK_CUDA_TRY(cudaStreamWaitEvent(h->solve, fork_ev, 0));
   h->next = 0;
   h->running = true;
+  h->trace = getenv("MUNK_TRACE_DIST") != nullptr;
+  h->tr.clear();
   return MUNK_OK;
 }
 
@@ -540,6 +570,19 @@ int munk_dist_potrf_end(munk_dist_t* h) {
   MUNK_CUDA_TRY(cudaEventRecord(join_ev, ws->side2));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(h->main, join_ev, 0));
   h->running = false;
+  if (h->trace) {
+    cudaStreamSynchronize(h->main);
+    fprintf(stderr, "dist potrf n=%d rank %d/%d: col owner | reach, LA_D, F, lan+TS_N, bcastA done, pieceB done (ms since start)\n",
+            h->n, h->rank, h->world);
+    for (int c = 0; c < h->nblk; ++c) {
+      float t[6];
+      for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], h->tr[0], h->tr[6 * c + i]);
+      fprintf(stderr, "  %3d %d | %8.3f %8.3f %8.3f %8.3f %8.3f %8.3f\n", c, owner_of(c, h->world), t[0], t[1], t[2], t[3],
+              t[4], t[5]);
+    }
+    for (cudaEvent_t e : h->tr) cudaEventDestroy(e);
+    h->tr.clear();
+  }
   return MUNK_OK;
 }
 

@@ -184,9 +184,19 @@ struct PotrfPlan {
     if (r0 == s(c)) return syrk_update(r, at(r0, s(c)), ld, r1 - r0, w, at(r0, s(c - 1)), at(s(c), s(c - 1)), ld, k);
     return gemm_update(r, at(r0, s(c)), ld, r1 - r0, w, at(r0, s(c - 1)), at(s(c), s(c - 1)), ld, k);
   }
-  // A[r0:r1, block column c] <- . L_cc^-T
+  // A[r0:r1, block column c] <- . L_cc^-T.  Few rows (the chain's TS_N): one strip-solve launch
+  // instead of the recursion's ~14 dependent small GEMMs.
   int ts(Rec& r, int r0, int r1, int c) {
-    return trsm_rec(r, at(r0, s(c)), ld, r1 - r0, at(s(c), s(c)), ld, s(c + 1) - s(c), s(c));
+    const int w = s(c + 1) - s(c);
+    static const int strip_rows = env_int("MUNK_STRIP_ROWS", 1024);
+    if (r1 - r0 > 0 && r1 - r0 <= strip_rows && w <= 512) {
+      MUNK_TRY(launch_trsm_strip(at(r0, s(c)), ld, r1 - r0, at(s(c), s(c)), ld, w,
+                                 linv + (long)(s(c) / LEAF) * LEAF * LEAF, r.stream));
+      ws->launches++;
+      ws->flops += (double)(r1 - r0) * w * w;
+      return MUNK_OK;
+    }
+    return trsm_rec(r, at(r0, s(c)), ld, r1 - r0, at(s(c), s(c)), ld, w, s(c));
   }
   void tick(cudaStream_t st) {
     if (!trace) return;
@@ -269,9 +279,9 @@ int potrf_lookahead(Workspace* ws, int n, double* A, long ld, double* linv, cuda
 // barely overlap (measured: together they take the sum of their separate times, 95 + 52 ms at
 // 20 000 / 16 000 columns) because a ready grid of the earlier stream always goes first; in one
 // stream the order is ours, and while one matrix waits for its latency-bound chain
-// (LA_D -> F -> TS_N) the other one's trailing update keeps the SMs busy.  `lead` > 1 lets the
-// second (smaller) matrix run ahead so that its latency-bound tail falls into the first one's
-// bulk phase.
+// (LA_D -> F -> TS_N) the other one's trailing update keeps the SMs busy.  `lead` > 1 would let
+// the second matrix run ahead of its share; measured at 20 000 / 16 000 columns: 137.7 ms with
+// lead 1.0, 142.3 with 1.3, 144.9 with 2.0 (separately: 95.6 + 51.8).
 int potrf_pair_lookahead(Workspace* wa, int na, double* A, long lda, double* linva, Workspace* wb, int nb,
                          double* B, long ldb, double* linvb, cudaStream_t main) {
   PotrfPlan pa(wa, na, A, lda, linva, main), pb(wb, nb, B, ldb, linvb, main);
@@ -280,7 +290,7 @@ int potrf_pair_lookahead(Workspace* wa, int na, double* A, long lda, double* lin
   double ta = 0, tb = 0, da = 0, db = 0;
   for (int c = 0; c < pa.nblk; ++c) ta += pa.work(c) + 1.0;
   for (int c = 0; c < pb.nblk; ++c) tb += pb.work(c) + 1.0;
-  static const double lead = env_int("MUNK_PAIR_LEAD_PCT", 130) / 100.0;
+  static const double lead = env_int("MUNK_PAIR_LEAD_PCT", 100) / 100.0;
   int ca = 0, cb = 0;
   while (ca < pa.nblk || cb < pb.nblk) {
     const bool take_b = cb < pb.nblk && (ca >= pa.nblk || db / tb <= lead * da / ta);
@@ -417,6 +427,13 @@ int trsm_left(Workspace* ws, int n, const double* L, long ld, const double* linv
 int trsm_right(Workspace* ws, int m, double* B, long ldb, const double* L, long ldl, int s,
                const double* linv, cudaStream_t stream) {
   if (m <= 0 || s <= 0) return MUNK_OK;
+  static const int strip_rows = env_int("MUNK_STRIP_ROWS", 1024);
+  if (m <= strip_rows && s <= 512) {
+    MUNK_TRY(launch_trsm_strip(B, ldb, m, L, ldl, s, linv, stream));
+    ws->launches++;
+    ws->flops += (double)m * s * s;
+    return MUNK_OK;
+  }
   Rec r{ws, stream, const_cast<double*>(linv), 0};
   return trsm_rec(r, B, ldb, m, L, ldl, s, 0);
 }

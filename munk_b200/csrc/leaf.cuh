@@ -10,4 +10,9 @@ namespace munk {
 int launch_potrf_leaf(double* A, long lda, int nb, double* Linv, int gidx, int* info,
                       cudaStream_t stream);
 
+// B (m x s, in place) <- B L^-T in one launch (trsm_strip.cu): L is s x s lower triangular,
+// s <= 512, `linv` holds the inverses of its 128 x 128 diagonal blocks (block k at linv + k*128*128).
+int launch_trsm_strip(double* B, long ldb, int m, const double* L, long ldl, int s, const double* linv,
+                      cudaStream_t stream);
+
 }  // namespace munk

@@ -281,11 +281,16 @@ def embed_device(n1, edges1, n2, edges2, landmark_idxs, src_lam=0.05, tgt_lam=0.
                 for t in (A2, linv2):
                     t.record_stream(hi)
                 ev[1].record()
-                W1 = dev.trtri(A1, n1, linv1)
-                ev[2].record()
-                flag1 = dev.potrf_info_async()
+            # the dense triangular inverse on the normal-priority stream, the latency-bound landmark
+            # solves on the high-priority one: their small kernels slot in at tile boundaries
             with torch.cuda.stream(lo):
                 lo.wait_event(ev[1])
+                W1 = dev.trtri(A1, n1, linv1)
+                for t in (A1, linv1):
+                    t.record_stream(lo)
+                ev[2].record()
+                flag1 = dev.potrf_info_async()
+            with torch.cuda.stream(hi):
                 B = dev2.target_landmark_rows_from_factor(A2, linv2, n2, t_idx)
                 ev[4].record()
                 flag2 = dev2.potrf_info_async()

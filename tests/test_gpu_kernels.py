@@ -437,3 +437,23 @@ def test_dist_factor_panel_major_single_rank(dev, n):
     fac.solve_backward(X2, X2.shape[1])
     D = torch.linalg.inv(torch.from_numpy(want_A).to(dev.torch_device))
     assert relerr(X2[:, :len(cols)], D[:, cols]) < 1e-11
+
+
+@pytest.mark.parametrize("m,s", [(1, 128), (37, 512), (300, 384), (1000, 300), (2500, 512)])
+def test_trsm_right_strip_and_recursive(dev, m, s):
+    """munk_trsm_right: B <- B L^-T.  Up to 1024 rows it is the one-launch strip solve
+    (trsm_strip.cu, also with a ragged last block), beyond that the recursion; both against torch."""
+    import torch
+    A0 = spd(s, 7)
+    A = dev.empty(s, s)
+    A[:, :s] = A0
+    linv = dev.potrf(A, s)
+    L = torch.tril(A[:, :s])
+    B0 = torch.randn(m, s, dtype=torch.float64, device="cuda")
+    guard = torch.full((m + 4, s + 16), 3.0, dtype=torch.float64, device="cuda")
+    B = guard[:m]
+    B[:, :s] = B0
+    dev.trsm_right(B, m, A, s, linv)
+    want = torch.linalg.solve_triangular(L, B0.t(), upper=False).t()
+    assert relerr(B[:, :s], want) < 1e-12
+    assert bool((guard[m:] == 3.0).all()) and bool((guard[:m, s:] == 3.0).all())

@@ -69,6 +69,14 @@ for p, t in pending.items():
     hom_mean, other_mean, diff = t if args.rank_k else t.cpu().numpy()[:3]
     local_res[p] = (diff, other_mean, hom_mean)
 table = permtest.gather_results(local_res, args.perms, rank, world, device=dev.torch_device)
+cross = None
+if rank == 0 and not args.rank_k:
+    # independent formulation (factored form, S never formed) on three of the permutations
+    cross = 0.0
+    for p in range(min(3, args.perms)):
+        a = np.array(pair.statistic_rank_k(permtest.permuted_homolog_idxs(homolog_idxs, p), k))
+        b = table[p][[2, 1, 0]]                       # (hom_mean, other_mean, diff)
+        cross = max(cross, float(np.max(np.abs(a - b) / np.abs(b))))
 if rank == 0:
     diffs = table[:, 0]
     pval, n_less, n_obs = permtest.one_tail_pval(real[2], diffs)
@@ -82,6 +90,7 @@ if rank == 0:
         "seconds_for_1000": 1000.0 / (args.perms / (float(ms) * 1e-3)),
         "setup_s_factor_both_graphs": t_setup,
         "real": {"hom_mean": float(real[0]), "other_mean": float(real[1]), "diff": float(real[2])},
+        "crosscheck_rank_k_max_rel_diff": cross,
         "pval": pval, "effect_size": float(permtest.effect_size(real[2], diffs)), "errs": int(np.isnan(diffs).sum()),
     }))
 if world > 1:
