@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "MUNK pipeline FP64 TFLOP/s (useful flops / pipeline s), 20k->16k nodes"
 UNIT = "TFLOP/s"
-# DRAM bytes (read + write) of the C3 score launch, ncu --set full, profiles/r01_ncu_summary.md
+# DRAM bytes (read + write) of the C3 score launch, ncu --set full, profiles/r02_ncu_summary.md
 NCU_SCORE_TRAFFIC_BYTES = 38.0e9
 
 
@@ -667,7 +667,7 @@ def run_gpu(args):
                          # dram__bytes_read.sum + dram__bytes_write.sum of this launch at C3 from the
                          # ncu --set full capture in profiles/ (null for other configs: not captured)
                          "traffic": NCU_SCORE_TRAFFIC_BYTES if args.config == "C3" else None,
-                         "traffic_source": "profiles/r01_ncu_summary.md (ncu --set full, one launch; algorithmic "
+                         "traffic_source": "profiles/r02_ncu_summary.md (ncu --set full, one launch; algorithmic "
                                            "bytes of the launch: %.2f GB)" % ((n1 * n1 / 2 + 2 * n1 * n2) * 8 / 1e9),
                          "kernel": "dgemm_dmma_tma_kernel<MC,MC> score launch: S = W1^T P, %d x %d x %d, "
                                    "k >= row only (%.2f TFLOP)" % (n1, n2, n1, fl["score"] / 1e12),
@@ -688,6 +688,84 @@ def run_gpu(args):
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def property_parity(out, dev, inp, n1, n2, rank, world):
+    """Parity of a configuration too large for a dense CPU reference (C5: 50 000 / 40 000 nodes;
+    the dense checker alone would take minutes of an 8-GPU lease): size-independent properties,
+    each evaluated with torch / cuBLAS operations on the sparse Laplacians and on random probe
+    vectors - none of this repo's kernels is involved in the checks.
+      factor      A1 (C1 C1^T v) = v for 4 random v: the row shards of C1 on all ranks really factor D1 = A1^-1
+      target_rows A2 B^T = E_Lt: B is D2[Lt,:] (checked on rank 0 from the projection's own input)
+      projection  C1[Ls,:] P = B: P = C2hat^T solves the landmark system (and lies in the row space by construction)
+      interpolation S[Ls,:] = B on the ranks that own landmark rows
+      product     S_r w = C1_r (P w) for 4 random w: every rank's score rows are C1_r C2hat^T
+    All residuals are relative to the largest entry of the right-hand side; tolerance 1e-8."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    tdev = dev.torch_device
+    rows = torch.as_tensor(np.asarray(out["rows"], dtype=np.int64), device=tdev)
+    C1, P, S = out["C1"], out["P"][:, :n2], out["S"][:, :n2]
+
+    def apply_A(edges, n, X, lam=0.05):
+        """(I + lam L) X from the edge list (sparse, torch index_add)."""
+        u = torch.as_tensor(np.asarray(edges[0], dtype=np.int64), device=tdev)
+        v = torch.as_tensor(np.asarray(edges[1], dtype=np.int64), device=tdev)
+        deg = torch.zeros(n, dtype=torch.float64, device=tdev)
+        deg.index_add_(0, u, torch.ones_like(u, dtype=torch.float64))
+        deg.index_add_(0, v, torch.ones_like(v, dtype=torch.float64))
+        Y = X * (1.0 + lam * deg)[:, None]
+        Y.index_add_(0, u, X[v], alpha=-lam)
+        Y.index_add_(0, v, X[u], alpha=-lam)
+        return Y
+
+    g = torch.Generator(device="cpu").manual_seed(7)
+    V = torch.randn(n1, 4, dtype=torch.float64, generator=g).to(tdev)
+    Wv = torch.randn(n2, 4, dtype=torch.float64, generator=g).to(tdev)
+    res = {}
+    # factor: t = C1^T v (sum over ranks of C1_r^T v_r), D1 v = C1 t (rows gathered), A1 (D1 v) = v
+    t = C1.t().contiguous() @ V[rows] if len(rows) else torch.zeros(n1, 4, dtype=torch.float64, device=tdev)
+    dist.all_reduce(t)
+    Dv = torch.zeros(n1, 4, dtype=torch.float64, device=tdev)
+    if len(rows):
+        Dv[rows] = C1 @ t
+    dist.all_reduce(Dv)
+    res["factor"] = float((apply_A(inp["edges1"], n1, Dv) - V).abs().max() / V.abs().max())
+    # target rows, projection: replicated inputs, checked on every rank (max over ranks below)
+    ls = torch.as_tensor([int(a) for a, _ in inp["landmark_idxs"]], device=tdev)
+    lt = torch.as_tensor([int(b) for _, b in inp["landmark_idxs"]], device=tdev)
+    # B = C1[Ls,:] P needs the landmark rows of C1: gather them from their owners
+    k = len(ls)
+    M = torch.zeros(k, n1, dtype=torch.float64, device=tdev)
+    pos = {int(r): i for i, r in enumerate(out["rows"])}
+    mine = [(i, pos[int(a)]) for i, a in enumerate(ls.tolist()) if int(a) in pos]
+    if mine:
+        M[torch.as_tensor([i for i, _ in mine], device=tdev)] = C1[torch.as_tensor([j for _, j in mine], device=tdev)]
+    dist.all_reduce(M)
+    B = M @ P                                                   # k x n2: what the projection reproduces
+    E = torch.zeros(n2, k, dtype=torch.float64, device=tdev)
+    E[lt, torch.arange(k, device=tdev)] = 1.0
+    res["target_rows_and_projection"] = float((apply_A(inp["edges2"], n2, B.t().contiguous()) - E).abs().max())
+    # interpolation on the owners of landmark rows; product on every rank
+    interp = torch.zeros(1, dtype=torch.float64, device=tdev)
+    if mine:
+        li = torch.as_tensor([i for i, _ in mine], device=tdev)
+        lj = torch.as_tensor([j for _, j in mine], device=tdev)
+        interp[0] = (S[lj] - B[li]).abs().max() / B.abs().max()
+    prod = torch.zeros(1, dtype=torch.float64, device=tdev)
+    if len(rows):
+        ref = C1 @ (P @ Wv)
+        prod[0] = (S @ Wv - ref).abs().max() / ref.abs().max()
+    both = torch.cat([interp, prod])
+    dist.all_reduce(both, op=dist.ReduceOp.MAX)
+    res["interpolation"], res["product"] = float(both[0]), float(both[1])
+    worst = torch.tensor([max(res.values())], dtype=torch.float64, device=tdev)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    return {"kind": "properties", "residuals": res, "max_residual": float(worst[0]), "tolerance": 1e-8,
+            "ok": bool(float(worst[0]) <= 1e-8),
+            "what": "size-independent properties over all %d ranks (see bench.py property_parity): the dense CPU "
+                    "checker is not run above 30 000 nodes" % world}
 
 
 def run_gpu_dist(args, dev, rank, world, local):
@@ -794,7 +872,9 @@ def run_gpu_dist(args, dev, rank, world, local):
     # of the host copies the e2e steps left in the ShardSink — against the CPU checker's S, which
     # rank 0 computes (no GPU data) and broadcasts
     parity = None
-    if not args.no_parity:
+    if not args.no_parity and (n1 > 30000 or args.parity_properties):
+        parity = property_parity(step(e1, e2), dev, inp, n1, n2, rank, world)
+    elif not args.no_parity:
         out = step(e1, e2)
         rows_t = torch.as_tensor(np.asarray(out["rows"], dtype=np.int64), device=tdev)
         S_ref = torch.empty((n1, n2), dtype=torch.float64, device=tdev)
@@ -887,6 +967,8 @@ def main():
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the CPU parity check")
     ap.add_argument("--no-api", dest="no_api", action="store_true", help="skip the api_e2e measurement")
+    ap.add_argument("--parity-properties", dest="parity_properties", action="store_true",
+                    help="N>1: use the size-independent property checks (default above 30 000 nodes) at any size")
     args = ap.parse_args()
     if args.impl == "reference":
         force_host_threads()

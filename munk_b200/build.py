@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libmunk_b200.so")
-SOURCES = ["api.cu", "dgemm.cu", "factor.cu", "leaf.cu", "trsm_strip.cu", "assemble.cu", "scores.cu", "jacobi.cu",
+SOURCES = ["api.cu", "dgemm.cu", "factor.cu", "leaf.cu", "diag.cu", "trsm_strip.cu", "assemble.cu", "scores.cu", "jacobi.cu",
            "dist.cu", "hostio.cu", "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

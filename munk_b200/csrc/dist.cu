@@ -232,7 +232,8 @@ int dist_step(munk_dist* h, int c) {
   cudaEvent_t* top_ev = diag_ev + nblk;      // piece A(c) complete on this rank
   cudaEvent_t* lan_ev = top_ev + nblk;
   cudaEvent_t* panel_ev = lan_ev + nblk;     // piece B(c) complete on this rank
-  cudaEvent_t* upd_ev = panel_ev + nblk;
+  cudaEvent_t* upd_ev = panel_ev + nblk;     // T(c) done on this rank
+  cudaEvent_t* upd1_ev = upd_ev + nblk;      // T(c) done for the first (lowest) block column this rank owns
   const bool multi = h->world > 1;
   auto rec = [&](cudaStream_t st, int scratch, int col) {
     Rec r{ws, st, h->linv(col), scratch};
@@ -274,11 +275,13 @@ int dist_step(munk_dist* h, int c) {
   // ---- chain stream
   h->tick(side);                                                     // 0: chain stream reaches column c
   if (h->own(c)) {
-    if (c >= 2) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, upd_ev[c - 2], 0));
+    // T(c-2) has to be finished for block column c only (the first one its loop touches), not for
+    // every block column this rank owns
+    if (c >= 2) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, upd1_ev[c - 2], 0));
     if (c >= 1) MUNK_TRY(la(side, 1, h->s(c), h->s(c + 1), c));
     h->tick(side);                                                   // 1: LA_D done
     Rec r = rec(side, 1, c);
-    MUNK_TRY(potrf_rec(r, h->rows(c, h->s(c)), h->ldp[c], h->w(c), 0));
+    MUNK_TRY(potrf_diag(r, h->rows(c, h->s(c)), h->ldp[c], h->w(c), 0));
     MUNK_CUDA_TRY(cudaEventRecord(diag_ev[c], side));
     h->tick(side);                                                   // 2: F done
     if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, lan_ev[c], 0));
@@ -310,7 +313,7 @@ int dist_step(munk_dist* h, int c) {
   MUNK_CUDA_TRY(cudaEventRecord(panel_ev[c], side2));
   h->tick(side2);                                                    // 5: piece B here
   if (h->own(c + 1)) {
-    if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, upd_ev[c - 1], 0));
+    if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, upd1_ev[c - 1], 0));
     MUNK_TRY(la(side2, 2, h->s(c + 2), h->s(c + 3), c + 1));
     MUNK_CUDA_TRY(cudaEventRecord(lan_ev[c + 1], side2));
     MUNK_TRY(la(side2, 2, h->s(c + 3), n, c + 1));
@@ -319,12 +322,16 @@ int dist_step(munk_dist* h, int c) {
   }
   // ---- caller's stream: panel c applied to this rank's block columns >= c + 2
   MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[c], 0));
+  bool first = true;
   for (int cc = c + 2; cc < nblk; ++cc) {
     if (!h->own(cc)) continue;
     Rec r = rec(main, 0, cc);
     const double* X = h->rows(c, h->s(cc));
     MUNK_TRY(syrk_update(r, h->rows(cc, h->s(cc)), h->ldp[cc], n - h->s(cc), h->w(cc), X, X, h->ldp[c], h->w(c)));
+    if (first) MUNK_CUDA_TRY(cudaEventRecord(upd1_ev[c], main));
+    first = false;
   }
+  if (first) MUNK_CUDA_TRY(cudaEventRecord(upd1_ev[c], main));
   MUNK_CUDA_TRY(cudaEventRecord(upd_ev[c], main));
   // ---- fused forward substitution with panel c
   if (h->X) {
@@ -525,9 +532,9 @@ int munk_dist_potrf_begin(munk_dist_t* h, void* stream_) {
   Workspace* ws = h->ws;
   DeviceGuard guard(ws->device);
   h->main = (cudaStream_t)stream_;
-  MUNK_TRY(ws->ensure_side(5 * (size_t)h->nblk + 2));
+  MUNK_TRY(ws->ensure_side(6 * (size_t)h->nblk + 2));
   for (int i = 0; i < 4; ++i) MUNK_TRY(ws->ensure_splitk(i, SPLITK_RESERVE));
-  cudaEvent_t fork_ev = ws->events[5 * h->nblk];
+  cudaEvent_t fork_ev = ws->events[6 * h->nblk];
   MUNK_CUDA_TRY(cudaEventRecord(fork_ev, h->main));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(ws->side, fork_ev, 0));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(ws->side2, fork_ev, 0));
@@ -559,7 +566,7 @@ int munk_dist_potrf_end(munk_dist_t* h) {
     MUNK_TRY(dist_step(h, h->next));
     h->next++;
   }
-  cudaEvent_t join_ev = ws->events[5 * h->nblk + 1];
+  cudaEvent_t join_ev = ws->events[6 * h->nblk + 1];
   MUNK_CUDA_TRY(cudaEventRecord(join_ev, ws->side));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(h->main, join_ev, 0));
   cudaEvent_t* panel_ev = ws->events.data() + 3 * h->nblk;

@@ -96,6 +96,28 @@ int potrf_rec(Rec& r, double* A, long ld, int n, int gidx) {
   return potrf_rec(r, A22, ld, n2, gidx + n1);
 }
 
+int potrf_diag(Rec& r, double* A, long ld, int w, int gidx) {
+  static const bool fused = env_int("MUNK_FUSED_DIAG", 1) != 0;
+  if (!fused || w % LEAF != 0 || w < 2 * LEAF) return potrf_rec(r, A, ld, w, gidx);
+  if (w <= 4 * LEAF) {
+    MUNK_TRY(launch_potrf_diag(A, ld, w, r.linv + (long)(gidx / LEAF) * LEAF * LEAF, r.stair_base + gidx,
+                               r.ws->info, reinterpret_cast<unsigned*>(r.ws->info + 4), r.stream));
+    r.ws->launches += 2;
+    r.ws->flops += (double)w * w * w / 3.0;
+    return MUNK_OK;
+  }
+  // wider (the 1024-column panels of the early block columns): two fused halves
+  const int n1 = 4 * LEAF, n2 = w - n1;
+  MUNK_TRY(potrf_diag(r, A, ld, n1, gidx));
+  double* A21 = A + (long)n1 * ld;
+  double* A22 = A21 + n1;
+  MUNK_TRY(launch_trsm_strip(A21, ld, n2, A, ld, n1, r.linv + (long)(gidx / LEAF) * LEAF * LEAF, r.stream));
+  r.ws->launches++;
+  r.ws->flops += (double)n2 * n1 * n1;
+  MUNK_TRY(syrk_update(r, A22, ld, n2, n2, A21, A21, ld, n1));
+  return potrf_diag(r, A22, ld, n2, gidx + n1);
+}
+
 // C (m x nc) -= X (m x k) Y (nc x k)^T, every tile (rows strictly below the diagonal block).
 int gemm_update(Rec& r, double* C, long ldc, int m, int nc, const double* X, const double* Y, long ldx,
                 int k) {
@@ -215,7 +237,7 @@ struct PotrfPlan {
     tick(side);
     if (c >= 1) MUNK_TRY(la(rs, s(c), s(c + 1), c));
     tick(side);
-    MUNK_TRY(potrf_rec(rs, at(s(c), s(c)), ld, s(c + 1) - s(c), s(c)));
+    MUNK_TRY(potrf_diag(rs, at(s(c), s(c)), ld, s(c + 1) - s(c), s(c)));
     MUNK_CUDA_TRY(cudaEventRecord(diag_ev[c], side));
     tick(side);
     if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, lan_ev[c], 0));

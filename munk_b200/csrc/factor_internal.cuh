@@ -35,6 +35,9 @@ inline int env_int(const char* name, int dflt) {
 
 // In-place Cholesky (+ leaf inverses into r.linv) of the n x n block whose first column is gidx.
 int potrf_rec(Rec& r, double* A, long ld, int n, int gidx);
+// The same for a diagonal block of the block-column drivers (w <= 1024): 512-column pieces go to
+// the one-launch kernel of diag.cu, anything else to the recursion.
+int potrf_diag(Rec& r, double* A, long ld, int w, int gidx);
 // B (m x s, in place) <- B L^-T, L the s x s lower block whose first column is gidx.
 int trsm_rec(Rec& r, double* B, long ldb, int m, const double* L, long ldl, int s, int gidx);
 // C (m x nc; top nc x nc part diagonal: lower tiles only) -= X Y^T, K = k

@@ -254,3 +254,24 @@ def test_benchmark_size_scores_match_independent_cpu_computation(m, cfg):
     W1 = torch.tril(emb.W1[:, :n1])
     ones1 = torch.ones(n1, dtype=torch.float64, device=W1.device)
     assert float((W1.t().mv(W1.mv(ones1)) - 1).abs().max()) < 1e-11
+
+
+def test_scores_reuses_device_embedding_only_for_untouched_outputs(m):
+    """munk.scores(C1, C2hat) on the arrays embed_networks just returned is served from the factors
+    still on the device; copies, other arrays and edited arrays go through the upload path.  Both
+    paths must give np.dot(source_X, target_X.T) (scripts/compute_embeddings.py:81)."""
+    import synth as synthetic
+    from munk_b200 import munk as impl
+    G1, G2, homs = synthetic.make_case(500, 420, 4, 60, seeds=(13, 14))
+    (C1, _), (C2, _), _, _ = m.embed_networks(G1, G2, homs, 30)
+    want = np.dot(C1, C2.T)
+    assert impl._cached_embedding(C1, C2) is not None
+    S = m.scores(C1, C2)
+    assert S.flags.writeable and S.flags.c_contiguous and oracle.rel_max_err(S, want) < 1e-12
+    assert impl._cached_embedding(C1.copy(), C2) is None and impl._cached_embedding(C1, C2.copy()) is None
+    assert oracle.rel_max_err(m.scores(C1.copy(), C2.copy()), want) < 1e-12
+    C1[0, 0] *= 3.0                                     # an in-place edit the fingerprint sees
+    assert impl._cached_embedding(C1, C2) is None
+    assert oracle.rel_max_err(m.scores(C1, C2), np.dot(C1, C2.T)) < 1e-12
+    m.release_device_cache()
+    assert impl._cache is None
