@@ -261,7 +261,9 @@ size_t munk_pinv_rows_work_bytes(int k);
  */
 int munk_dist_block(void);
 int munk_comm_unique_id(void* id128);
-int munk_comm_create(int device, int rank, int world, const void* id128, munk_comm_t** comm);
+/* max_ctas > 0 caps the SMs one collective of this communicator may occupy (ncclConfig_t.maxCTAs);
+ * 0 leaves NCCL's default. */
+int munk_comm_create(int device, int rank, int world, const void* id128, int max_ctas, munk_comm_t** comm);
 int munk_comm_destroy(munk_comm_t* comm);
 
 /*
@@ -271,7 +273,10 @@ int munk_comm_destroy(munk_comm_t* comm);
  * 16-byte aligned, owned by the caller, and must outlive the handle.  comm = NULL: one rank.
  */
 size_t munk_dist_storage_elems(int n);
-int munk_dist_create(munk_workspace_t* ws, munk_comm_t* comm, int n, double* storage, munk_dist_t** dist);
+/* `bulk` (may be NULL = use `comm`): a second communicator of the same ranks for the large part of
+ * every panel, so that the next panel's small critical piece never queues behind 70 MB. */
+int munk_dist_create(munk_workspace_t* ws, munk_comm_t* comm, munk_comm_t* bulk, int n, double* storage,
+                     munk_dist_t** dist);
 int munk_dist_destroy(munk_dist_t* dist);
 int munk_dist_blocks(munk_dist_t* dist);
 

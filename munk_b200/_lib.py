@@ -65,10 +65,10 @@ SIGNATURES = {
     "munk_pinv_rows_work_bytes": (c_size_t, [c_int]),
     "munk_dist_block": (c_int, []),
     "munk_comm_unique_id": (c_int, [c_void_p]),
-    "munk_comm_create": (c_int, [c_int, c_int, c_int, c_void_p, _P(c_void_p)]),
+    "munk_comm_create": (c_int, [c_int, c_int, c_int, c_void_p, c_int, _P(c_void_p)]),
     "munk_comm_destroy": (c_int, [c_void_p]),
     "munk_dist_storage_elems": (c_size_t, [c_int]),
-    "munk_dist_create": (c_int, [c_void_p, c_void_p, c_int, c_void_p, _P(c_void_p)]),
+    "munk_dist_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, _P(c_void_p)]),
     "munk_dist_destroy": (c_int, [c_void_p]),
     "munk_dist_blocks": (c_int, [c_void_p]),
     "munk_dist_assemble": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p]),

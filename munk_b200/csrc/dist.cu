@@ -56,6 +56,7 @@ struct NcclApi {
   bool ok = false;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;   // optional
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -70,6 +71,7 @@ NcclApi& nccl() {
     if (!h) return a;
     a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
     a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+    a.CommInitRankConfig = (decltype(a.CommInitRankConfig))dlsym(h, "ncclCommInitRankConfig");
     a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
     a.Broadcast = (decltype(a.Broadcast))dlsym(h, "ncclBroadcast");
     a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
@@ -168,7 +170,8 @@ struct munk_comm {
 
 struct munk_dist {
   Workspace* ws = nullptr;
-  munk_comm* comm = nullptr;
+  munk_comm* comm = nullptr;        // chain communicator: the small piece A(c) of every panel
+  munk_comm* bulk = nullptr;        // bulk communicator: the rest of the panel (never queues ahead of a piece A)
   int rank = 0, world = 1, n = 0, nblk = 0;
   std::vector<int> start;                 // nblk + 1
   std::vector<int> ldp;                   // leading dimension of panel c
@@ -234,6 +237,7 @@ int dist_step(munk_dist* h, int c) {
   cudaEvent_t* panel_ev = lan_ev + nblk;     // piece B(c) complete on this rank
   cudaEvent_t* upd_ev = panel_ev + nblk;     // T(c) done on this rank
   cudaEvent_t* upd1_ev = upd_ev + nblk;      // T(c) done for the first (lowest) block column this rank owns
+  cudaEvent_t* top2_ev = upd1_ev + nblk;     // panel c-2 applied to block column c (depth-2 look-ahead, owner of c)
   const bool multi = h->world > 1;
   auto rec = [&](cudaStream_t st, int scratch, int col) {
     Rec r{ws, st, h->linv(col), scratch};
@@ -275,9 +279,9 @@ int dist_step(munk_dist* h, int c) {
   // ---- chain stream
   h->tick(side);                                                     // 0: chain stream reaches column c
   if (h->own(c)) {
-    // T(c-2) has to be finished for block column c only (the first one its loop touches), not for
-    // every block column this rank owns
-    if (c >= 2) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, upd1_ev[c - 2], 0));
+    // panel c-2 reaches block column c through the panel stream (below), not through the FIFO
+    // of this rank's trailing updates
+    if (c >= 2) MUNK_CUDA_TRY(cudaStreamWaitEvent(side, top2_ev[c], 0));
     if (c >= 1) MUNK_TRY(la(side, 1, h->s(c), h->s(c + 1), c));
     h->tick(side);                                                   // 1: LA_D done
     Rec r = rec(side, 1, c);
@@ -304,26 +308,41 @@ int dist_step(munk_dist* h, int c) {
     MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, diag_ev[c], 0));
     MUNK_TRY(ts(side2, 2, h->s(c + 2), n, c));
   }
+  // (a receiver starts its part of the broadcast only once piece A(c) is here: until then the root
+  // is still factoring, and a waiting NCCL kernel would hold SMs for nothing)
   MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, top_ev[c], 0));
   if (multi && h->s(c + 2) < n) {
+    // piece B(c) on the bulk communicator: a later piece A never waits behind it
     const size_t count = (size_t)(n - h->s(c + 2)) * h->ldp[c];
     double* p = h->rows(c, h->s(c + 2));
-    MUNK_NCCL_TRY(nccl().Broadcast(p, p, count, ncclDouble, owner_of(c, h->world), h->comm->comm, side2));
+    MUNK_NCCL_TRY(nccl().Broadcast(p, p, count, ncclDouble, owner_of(c, h->world), h->bulk->comm, side2));
   }
   MUNK_CUDA_TRY(cudaEventRecord(panel_ev[c], side2));
   h->tick(side2);                                                    // 5: piece B here
   if (h->own(c + 1)) {
-    if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, upd1_ev[c - 1], 0));
+    // block column c+1 already holds panel c-1 (depth-2 look-ahead of step c-1, this stream)
     MUNK_TRY(la(side2, 2, h->s(c + 2), h->s(c + 3), c + 1));
     MUNK_CUDA_TRY(cudaEventRecord(lan_ev[c + 1], side2));
     MUNK_TRY(la(side2, 2, h->s(c + 3), n, c + 1));
   } else if (c + 1 < nblk) {
     MUNK_CUDA_TRY(cudaEventRecord(lan_ev[c + 1], side2));      // keeps the event defined on every rank
   }
-  // ---- caller's stream: panel c applied to this rank's block columns >= c + 2
+  // ---- depth-2 look-ahead: the owner of block column c+2 applies panel c to it on the panel
+  // stream, the moment piece B(c) is here, instead of queueing it behind the trailing updates of
+  // its other block columns (measured at 8 GPUs: the next-but-one owner's chain waited 1-2 ms per
+  // block column for exactly this update, profiles/r02_dist_trace_n8_fused.log)
+  if (h->own(c + 2)) {
+    if (c >= 1) MUNK_CUDA_TRY(cudaStreamWaitEvent(side2, upd1_ev[c - 1], 0));   // T(c-1) has left column c+2
+    Rec r = rec(side2, 2, c + 2);
+    const double* X = h->rows(c, h->s(c + 2));
+    MUNK_TRY(syrk_update(r, h->rows(c + 2, h->s(c + 2)), h->ldp[c + 2], n - h->s(c + 2), h->w(c + 2), X, X, h->ldp[c],
+                         h->w(c)));
+    MUNK_CUDA_TRY(cudaEventRecord(top2_ev[c + 2], side2));
+  }
+  // ---- caller's stream: panel c applied to this rank's block columns >= c + 3
   MUNK_CUDA_TRY(cudaStreamWaitEvent(main, panel_ev[c], 0));
   bool first = true;
-  for (int cc = c + 2; cc < nblk; ++cc) {
+  for (int cc = c + 3; cc < nblk; ++cc) {
     if (!h->own(cc)) continue;
     Rec r = rec(main, 0, cc);
     const double* X = h->rows(c, h->s(cc));
@@ -375,7 +394,7 @@ int munk_comm_unique_id(void* id128) {
   return MUNK_OK;
 }
 
-int munk_comm_create(int device, int rank, int world, const void* id128, munk_comm_t** out) {
+int munk_comm_create(int device, int rank, int world, const void* id128, int max_ctas, munk_comm_t** out) {
   if (!out) return -5;
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) return -2;
@@ -392,7 +411,19 @@ int munk_comm_create(int device, int rank, int world, const void* id128, munk_co
     DeviceGuard guard(device);
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    ncclResult_t r = nccl().CommInitRank(&c->comm, world, id, rank);
+    // A collective's kernel occupies one SM per CTA from the moment it is launched until its data
+    // has arrived - on the receivers that is the whole time the root still computes - and an SM
+    // that holds an NCCL CTA cannot hold a GEMM tile.  The panel pieces are small (MBs): a few
+    // CTAs move them at link speed, so the communicator is capped (max_ctas > 0).
+    ncclResult_t r = ncclInvalidUsage;
+    if (max_ctas > 0 && nccl().CommInitRankConfig) {
+      ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+      cfg.minCTAs = 1;
+      cfg.maxCTAs = max_ctas;
+      r = nccl().CommInitRankConfig(&c->comm, world, id, rank, &cfg);
+      if (r != ncclSuccess) c->comm = nullptr;
+    }
+    if (r != ncclSuccess) r = nccl().CommInitRank(&c->comm, world, id, rank);
     if (r != ncclSuccess) {
       set_last_error("ncclCommInitRank failed: %s", nccl().GetErrorString(r));
       delete c;
@@ -421,7 +452,8 @@ size_t munk_dist_storage_elems(int n) {
   return (size_t)total;
 }
 
-int munk_dist_create(munk_workspace_t* wsp, munk_comm_t* comm, int n, double* storage, munk_dist_t** out) {
+int munk_dist_create(munk_workspace_t* wsp, munk_comm_t* comm, munk_comm_t* bulk, int n, double* storage,
+                     munk_dist_t** out) {
   Workspace* ws = reinterpret_cast<Workspace*>(wsp);
   if (!ws) return -1;
   if (n <= 0) return -3;
@@ -431,7 +463,7 @@ int munk_dist_create(munk_workspace_t* wsp, munk_comm_t* comm, int n, double* st
   DeviceGuard guard(ws->device);
   munk_dist* h = new (std::nothrow) munk_dist();
   if (!h) return -5;
-  h->ws = ws; h->comm = comm;
+  h->ws = ws; h->comm = comm; h->bulk = bulk ? bulk : comm;
   h->rank = comm ? comm->rank : 0;
   h->world = comm ? comm->world : 1;
   h->n = n; h->storage = storage;
@@ -532,9 +564,9 @@ int munk_dist_potrf_begin(munk_dist_t* h, void* stream_) {
   Workspace* ws = h->ws;
   DeviceGuard guard(ws->device);
   h->main = (cudaStream_t)stream_;
-  MUNK_TRY(ws->ensure_side(6 * (size_t)h->nblk + 2));
+  MUNK_TRY(ws->ensure_side(7 * (size_t)h->nblk + 2));
   for (int i = 0; i < 4; ++i) MUNK_TRY(ws->ensure_splitk(i, SPLITK_RESERVE));
-  cudaEvent_t fork_ev = ws->events[6 * h->nblk];
+  cudaEvent_t fork_ev = ws->events[7 * h->nblk];
   MUNK_CUDA_TRY(cudaEventRecord(fork_ev, h->main));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(ws->side, fork_ev, 0));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(ws->side2, fork_ev, 0));
@@ -566,7 +598,7 @@ int munk_dist_potrf_end(munk_dist_t* h) {
     MUNK_TRY(dist_step(h, h->next));
     h->next++;
   }
-  cudaEvent_t join_ev = ws->events[6 * h->nblk + 1];
+  cudaEvent_t join_ev = ws->events[7 * h->nblk + 1];
   MUNK_CUDA_TRY(cudaEventRecord(join_ev, ws->side));
   MUNK_CUDA_TRY(cudaStreamWaitEvent(h->main, join_ev, 0));
   cudaEvent_t* panel_ev = ws->events.data() + 3 * h->nblk;

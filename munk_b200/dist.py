@@ -204,7 +204,7 @@ class DistComm:
     """An NCCL communicator owned by the C library (munk_comm_*), one per concurrently running
     factorisation.  Creation is collective: rank 0's unique id travels through torch.distributed."""
 
-    def __init__(self, dev, rank, world, group=None):
+    def __init__(self, dev, rank, world, group=None, max_ctas=0):
         self.rank, self.world = rank, world
         self._h = ctypes.c_void_p()
         ident = torch.zeros(128, dtype=torch.uint8, device=dev.torch_device)
@@ -216,7 +216,8 @@ class DistComm:
             dist.broadcast(ident, src=_global_rank(group, 0), group=group)
         raw = bytes(ident.cpu().numpy().tobytes())
         with torch.cuda.device(dev.index):
-            check(lib.munk_comm_create(dev.index, rank, world, raw, ctypes.byref(self._h)), "munk_comm_create")
+            check(lib.munk_comm_create(dev.index, rank, world, raw, int(max_ctas), ctypes.byref(self._h)),
+                  "munk_comm_create")
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -234,13 +235,14 @@ class DistFactor:
     block columns, the stepwise factorisation with an optional fused forward substitution, the
     backward substitution and an unpack into an ordinary lower-triangular matrix (tests)."""
 
-    def __init__(self, dev, comm, n):
+    def __init__(self, dev, comm, n, bulk=None):
         assert lib.munk_dist_block() == NB
-        self.dev, self.comm, self.n = dev, comm, int(n)
+        self.dev, self.comm, self.bulk, self.n = dev, comm, bulk, int(n)
         self.storage = torch.empty(lib.munk_dist_storage_elems(self.n), dtype=torch.float64,
                                    device=dev.torch_device)
         self._h = ctypes.c_void_p()
-        check(lib.munk_dist_create(dev._ws, comm._h if comm is not None else None, self.n,
+        check(lib.munk_dist_create(dev._ws, comm._h if comm is not None else None,
+                                   bulk._h if bulk is not None else None, self.n,
                                    ctypes.c_void_p(self.storage.data_ptr()), ctypes.byref(self._h)),
               "munk_dist_create")
         self._keep = None
@@ -314,7 +316,13 @@ def onehot_rhs(n, cols, device):
 
 
 _DIST = {}
-_THREADS = os.environ.get("MUNK_DIST_THREADS", "1") != "0"
+# One host thread by default: NCCL orders kernel launches of all communicators of a device in host
+# issue order, so every rank must issue the collectives of the two chains in the SAME order; two
+# threads make that order racy (observed: one hang in ~10 runs at 2 GPUs) and bought nothing
+# (101.0 vs 101.3 ms at 8 GPUs).  MUNK_DIST_THREADS=1 keeps the experiment available.
+_THREADS = os.environ.get("MUNK_DIST_THREADS", "0") == "1"
+_CHAIN_CTAS = int(os.environ.get("MUNK_NCCL_CHAIN_CTAS", "4"))
+_BULK_CTAS = int(os.environ.get("MUNK_NCCL_BULK_CTAS", "8"))
 
 
 def _dist_resources(dev, n1, n2, rank, world, group):
@@ -326,10 +334,13 @@ def _dist_resources(dev, n1, n2, rank, world, group):
     if res is None:
         from .device import Device
         dev2 = Device(dev.index)
-        comm1 = DistComm(dev, rank, world, group) if world > 1 else None
-        comm2 = DistComm(dev, rank, world, group) if world > 1 else None
-        res = _DIST[key] = dict(dev2=dev2, side=torch.cuda.Stream(device=dev.index), comm1=comm1, comm2=comm2,
-                                fac1=DistFactor(dev, comm1, n1), fac2=DistFactor(dev2, comm2, n2))
+        # per chain: one communicator for the small critical piece of every panel, one for the bulk
+        # (SM caps: a few CTAs move a 5 MB piece at link speed; the bulk gets more)
+        caps = [_CHAIN_CTAS, _BULK_CTAS, _CHAIN_CTAS, _BULK_CTAS]
+        comms = [DistComm(dev, rank, world, group, max_ctas=cap) if world > 1 else None for cap in caps]
+        res = _DIST[key] = dict(dev2=dev2, side=torch.cuda.Stream(device=dev.index), comms=comms,
+                                fac1=DistFactor(dev, comms[0], n1, bulk=comms[1]),
+                                fac2=DistFactor(dev2, comms[2], n2, bulk=comms[3]))
     return res
 
 
@@ -490,8 +501,8 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
     #    (csrc/dist.cu).  Source: X = [my columns of W1 | landmark columns Q1] (staircase one-hot
     #    right-hand side).  Target: the k landmark columns of the identity.  The chains are
     #    independent and latency-bound in their block-column chain, so they run concurrently: own
-    #    stream, own workspace, own NCCL communicator, and - because every block column costs the
-    #    host ~100 launches - own host thread (the C calls release the GIL).
+    #    stream, own workspace, own NCCL communicators; one host thread interleaves their block
+    #    columns so that every rank issues all collectives in the same order.
     main = torch.cuda.current_stream(dev.index)
     res = _dist_resources(dev, n1, n2, rank, world, group)
     dev2, side, fac1, fac2 = res["dev2"], res["side"], res["fac1"], res["fac2"]
