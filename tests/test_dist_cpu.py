@@ -169,3 +169,18 @@ def test_distributed_cholesky_schedule_two_ranks_gloo():
     for o in outs:
         bad, err = o.split()
         assert int(bad) == 0 and float(err) < 1e-12
+
+
+def test_onehot_rhs_columns_and_staircase():
+    """Right-hand side of the target's fused forward substitution: one-hot columns in landmark-list
+    order (repeats allowed), staircase = first non-zero row of each 128-column tile."""
+    import torch
+    from munk_b200.dist import onehot_rhs
+    cols = [700, 5, 5, 999] + list(range(300, 430))
+    X, stair = onehot_rhs(1000, cols, torch.device("cpu"))
+    assert X.shape == (1000, 256) and stair.tolist() == [5, 424]
+    assert float(X.sum()) == len(cols)
+    for l, c in enumerate(cols):
+        assert X[c, l] == 1.0
+    X0, stair0 = onehot_rhs(64, [], torch.device("cpu"))
+    assert X0.shape == (64, 128) and stair0.tolist() == [64] and float(X0.abs().sum()) == 0.0
