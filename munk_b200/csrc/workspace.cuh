@@ -41,11 +41,17 @@ struct Workspace {
 
   int ensure(double** p, size_t* cur, size_t need) {
     if (*cur >= need) return MUNK_OK;
+    // a buffer is about to move: captured graphs hold its old address
+    if (*p) drop_graphs();
     if (*p) MUNK_CUDA_TRY(cudaFree(*p));
     *p = nullptr; *cur = 0;
     MUNK_CUDA_TRY(cudaMalloc((void**)p, need));
     *cur = need;
     return MUNK_OK;
+  }
+  void drop_graphs() {
+    for (GraphEntry& g : graphs)
+      if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
   }
   int ensure_splitk(int which, size_t need) { return ensure(&splitk[which], &splitk_bytes[which], need); }
 

@@ -457,3 +457,30 @@ def test_trsm_right_strip_and_recursive(dev, m, s):
     want = torch.linalg.solve_triangular(L, B0.t(), upper=False).t()
     assert relerr(B[:, :s], want) < 1e-12
     assert bool((guard[m:] == 3.0).all()) and bool((guard[:m, s:] == 3.0).all())
+
+
+def test_graph_replay_survives_workspace_growth():
+    """Factorisations of >= 4096 columns replay cached CUDA graphs from their second use on
+    (factor.cu graph_or_direct).  A larger matrix on the same workspace moves the triangular-inverse
+    temporary: the cached graphs must be dropped, not replayed with a dangling address."""
+    import torch
+    from munk_b200.device import Device
+    d = Device(0)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        def run(A0, A, linv, n):
+            A[:, :n] = A0
+            d.potrf(A, n, linv=linv, check_info=False)
+            d.trtri(A, n, linv)
+            W = torch.tril(A[:, :n])
+            x = torch.ones(n, 3, dtype=torch.float64, device="cuda")
+            return float((W.t() @ (W @ (A0 @ x)) - x).abs().max())       # W^T W = A0^-1
+        small, big = 4224, 5000
+        As, Ab = spd(small, 1), spd(big, 2)
+        bufs = d.empty(small, small), d.new_linv(small)
+        bufb = d.empty(big, big), d.new_linv(big)
+        errs = [run(As, *bufs, small) for _ in range(3)]                # direct, capture, replay
+        errs += [run(Ab, *bufb, big) for _ in range(3)]                 # grows the temporary
+        errs += [run(As, *bufs, small) for _ in range(3)]               # re-capture, replay
+        assert d.potrf_info() == 0
+    assert max(errs) < 1e-10, errs
