@@ -40,7 +40,7 @@ import torch
 import torch.distributed as dist
 
 from ._lib import check, lib
-from .device import KC, MC, TILE_LOWER, pad16, landmark_groups
+from .device import MC, pad16, landmark_groups
 
 NB = 512
 
@@ -75,29 +75,10 @@ class ColumnCyclic:
         return out
 
 
-class CudaOps:
-    """The four operations of the distributed Cholesky on a munk_b200 Device."""
-
-    def __init__(self, dev):
-        self.dev = dev
-        self.device = dev.torch_device
-
-    def syrk_lower(self, C, X, Y, m, nc, k):
-        """C[:m, :nc] -= X[:m, :k] Y[:nc, :k]^T (at least the tiles touching the lower triangle)."""
-        self.dev.gemm(KC, KC, m, nc, k, -1.0, X, Y, 1.0, C, TILE_LOWER)
-
-    def factor_panel(self, A, n, c0, w, linv):
-        """In place: Cholesky of the w x w diagonal block at (c0, c0) and the panel solve below."""
-        diag = A[c0:, c0:]
-        lv = linv[(c0 // 128) * 128 * 128:]
-        self.dev.potrf(diag, w, linv=lv, check_info=False)
-        below = n - (c0 + w)
-        if below > 0:
-            self.dev.trsm_right(A[c0 + w:, c0:], below, diag, w, lv)
-
-    def info(self):
-        return self.dev.potrf_info()
-
+# `ops` protocol of the schedule specification below (tests/cpu_ops.py implements it on torch CPU
+# tensors): syrk_lower(C, X, Y, m, nc, k): C[:m,:nc] -= X[:m,:k] Y[:nc,:k]^T on the lower tiles;
+# factor_panel(A, n, c0, w, linv): Cholesky of the w x w diagonal block at (c0, c0) + panel solve
+# below it; info(): the non-SPD flag.
 
 def _panel_elems(n, c0, w):
     ldp = pad16(w)
@@ -344,25 +325,6 @@ def _dist_resources(dev, n1, n2, rank, world, group):
     return res
 
 
-_SIDE = {}
-
-
-def _side_resources(dev, world, group):
-    """(second Device/workspace, second stream, second communicator) of this process for work
-    that runs concurrently with the main chain; created once.  Collective on first call when
-    world > 1 (dist.new_group)."""
-    key = (dev.index, id(group))
-    res = _SIDE.get(key)
-    if res is None:
-        from .device import Device
-        group2 = None
-        if world > 1:
-            ranks = list(range(world)) if group is None else dist.get_process_group_ranks(group)
-            group2 = dist.new_group(ranks=ranks)
-        res = _SIDE[key] = (Device(dev.index), torch.cuda.Stream(device=dev.index), group2)
-    return res
-
-
 def _global_rank(group, group_rank):
     if group is None:
         return group_rank
@@ -477,7 +439,6 @@ def dist_embed_scores(dev, n1, edges1, n2, edges2, landmark_idxs, rank, world, g
        P      (n1, n2) C2hat^T, replicated                        (CUDA tensor, padded ld)
        S      (len(rows), n2) rows of the score matrix            (CUDA tensor)
        stats  (hom_mean, other_mean, diff) over the full matrix if homolog_idxs is given."""
-    ops = CudaOps(dev)
 
     def mark(name):
         if marks is not None:

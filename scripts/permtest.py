@@ -29,7 +29,6 @@ import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 
-import munk_b200 as munk  # noqa: E402
 from munk_b200 import permtest, util  # noqa: E402
 from munk_b200.io import get_logger  # noqa: E402
 

@@ -1,4 +1,4 @@
-"""torch-CPU stand-in for munk_b200.dist.CudaOps — TEST INFRASTRUCTURE ONLY.
+"""torch-CPU implementation of the `ops` protocol of munk_b200.dist.dist_potrf_steps (the schedule specification) — TEST INFRASTRUCTURE ONLY.
 
 Lets the multi-rank schedule of munk_b200.dist.dist_potrf (ownership map, look-ahead order,
 packing, broadcasts) run under gloo on CPU tensors.  It is never imported by the product."""
