@@ -187,6 +187,16 @@ int munk_download_block(int rows, int cols, const double* C, long ldc, double* h
 int munk_download_pageable(int device, long rows, long cols, const double* src, long lds, double* host,
                            long ldh, int upper, int threads, void* stream);
 
+/*
+ * 128-bit content digest of a HOST buffer (no device work): out[0] = position-dependent polynomial
+ * hash of the 64-bit words (any one-word change always changes it), out[1] = sum of the words.
+ * `threads` host threads read the buffer at memory-bus speed; the result does not depend on the
+ * thread count.  munk.scores() uses it to decide whether the arrays it is handed are, byte for byte,
+ * the ones munk.embed_networks returned (so that np.dot(source_X, target_X.T),
+ * scripts/compute_embeddings.py:72-81, can be served from the factors still on the device).
+ */
+int munk_host_digest(const void* data, size_t bytes, int threads, unsigned long long* out);
+
 /* out[g][:] = mean of in[members[gptr[g] .. gptr[g+1])][:]; used to fold duplicated source
  * landmarks (np.linalg.pinv's minimum-norm least-squares answer, munk/munk/munk.py:109). */
 int munk_group_mean_rows(int ngroups, const int* gptr, const int* members, int ncols,

@@ -54,6 +54,7 @@ SIGNATURES = {
     "munk_download_block": (c_int, [c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p]),
     "munk_download_pageable": (c_int, [c_int, c_long, c_long, c_void_p, c_long, c_void_p, c_long, c_int, c_int,
                                        c_void_p]),
+    "munk_host_digest": (c_int, [c_void_p, c_size_t, c_int, c_void_p]),
     "munk_separate_scores": (c_int, [c_int, c_int, c_void_p, c_long] + [c_void_p] * 13 + [c_void_p]),
     "munk_separate_scores_means": (c_int, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_int,
                                            c_void_p, c_void_p, c_double, c_void_p, c_void_p,

@@ -126,3 +126,81 @@ extern "C" int munk_download_pageable(int device, long rows, long cols, const do
   }
   return MUNK_OK;
 }
+
+
+// ---- content digest of a host buffer --------------------------------------------------------------
+// munk.scores() serves np.dot(source_X, target_X.T) from the factors still on the device when it is
+// handed the very arrays embed_networks returned (scripts/compute_embeddings.py:72-81).  "The very
+// arrays" has to include their contents: the caller owns them and may have edited them in place.
+// This digest is taken when the arrays are returned and again when they come back; it reads every
+// byte (T threads, memory-bus speed) instead of sampling.
+//   chunk (8 MB) digest: four interleaved polynomial hashes h <- h K + w (mod 2^64) over the 64-bit
+//   words, folded with an odd multiplier; buffer digest: the chunk digests folded in order (so the
+//   result does not depend on the thread count).  Every multiplier is odd, hence invertible mod
+//   2^64: changing any single word by d != 0 changes the digest by d * odd != 0 - a one-element
+//   edit is always seen; anything else with probability 1 - 2^-64.  out[1] = plain sum of the words.
+namespace {
+
+constexpr size_t DIGEST_CHUNK = (size_t)8 << 20;
+constexpr unsigned long long DK = 0x9E3779B97F4A7C15ull, DK1 = 0xC2B2AE3D27D4EB4Full, DK2 = 0x165667B19E3779F9ull;
+
+void digest_chunk(const unsigned char* p, size_t bytes, unsigned long long* poly, unsigned long long* sum) {
+  unsigned long long h0 = 1, h1 = 2, h2 = 3, h3 = 4, s = 0;
+  const size_t words = bytes / 8;
+  size_t i = 0;
+  for (; i + 4 <= words; i += 4) {
+    unsigned long long w[4];
+    memcpy(w, p + 8 * i, 32);
+    h0 = h0 * DK + w[0];
+    h1 = h1 * DK + w[1];
+    h2 = h2 * DK + w[2];
+    h3 = h3 * DK + w[3];
+    s += w[0] + w[1] + w[2] + w[3];
+  }
+  for (; i < words; ++i) {
+    unsigned long long w;
+    memcpy(&w, p + 8 * i, 8);
+    h0 = h0 * DK + w;
+    s += w;
+  }
+  if (bytes & 7) {
+    unsigned long long w = 0;
+    memcpy(&w, p + 8 * words, bytes & 7);
+    h1 = h1 * DK + w;
+    s += w;
+  }
+  *poly = ((h0 * DK1 + h1) * DK1 + h2) * DK1 + h3;
+  *sum = s;
+}
+
+}  // namespace
+
+extern "C" int munk_host_digest(const void* data, size_t bytes, int threads, unsigned long long* out) {
+  if (!data && bytes) return -1;
+  if (!out) return -4;
+  const size_t nchunks = (bytes + DIGEST_CHUNK - 1) / DIGEST_CHUNK;
+  threads = (int)std::max<size_t>(1, std::min<size_t>({(size_t)std::max(threads, 1), (size_t)64, std::max<size_t>(nchunks, 1)}));
+  std::vector<unsigned long long> poly(nchunks), sum(nchunks);
+  std::atomic<size_t> next(0);
+  const unsigned char* base = static_cast<const unsigned char*>(data);
+  auto work = [&]() {
+    for (;;) {
+      const size_t c = next.fetch_add(1);
+      if (c >= nchunks) return;
+      const size_t off = c * DIGEST_CHUNK;
+      digest_chunk(base + off, std::min(DIGEST_CHUNK, bytes - off), &poly[c], &sum[c]);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+  work();
+  for (std::thread& th : pool) th.join();
+  unsigned long long h = bytes, s = 0;
+  for (size_t c = 0; c < nchunks; ++c) {
+    h = h * DK2 + poly[c];
+    s += sum[c];
+  }
+  out[0] = h;
+  out[1] = s;
+  return MUNK_OK;
+}

@@ -5,12 +5,17 @@ in hand-written sm_100a kernels behind include/munk_b200.h.  Inputs and outputs 
 are host numpy arrays (the reference's contract); `munk_b200.pipeline` keeps everything on the
 device for callers that chain the stages.
 """
+import ctypes
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import joblib
 import numpy as np
 import torch
 
 from . import util
-from .device import KC, MC, default_device, landmark_groups, NotPositiveDefinite
+from ._lib import lib, check
+from .device import KC, MC, default_device, landmark_groups
 from .pipeline import embed_device, graph_inputs
 from .scores_plan import plan_separate_scores
 
@@ -82,17 +87,26 @@ def embed_matrices(source_C, target_D, landmark_idxs):
 # The last embedding embed_networks() produced stays on the device, so that the reference's next
 # step - np.dot(source_X, target_X.T) on the arrays it just returned
 # (scripts/compute_embeddings.py:72-81) - does not send 5.8 GB back up.  scores() uses it only for
-# the very arrays that embedding returned (object identity) and only if they are unchanged: a
-# fingerprint (every 4099th element of either array, taken when they were returned) is compared
-# first.  An in-place edit that touches none of the sampled elements is not noticed; copy the array
-# (or call release_device_cache()) before editing embeddings in place.
+# the very arrays that embedding returned (object identity) and only if their contents are
+# unchanged: a 128-bit digest of every byte of either array (munk_host_digest: all host threads,
+# memory-bus speed, any one-element edit is always seen) is taken when they are returned and again
+# when they come back.  Edited arrays, copies and anything else go through the upload path.
 _cache = None
-_FP_STRIDE = 4099
 
 
-def _fingerprint(arr):
-    flat = arr.reshape(-1) if arr.flags.c_contiguous else arr.T.reshape(-1)
-    return flat[::_FP_STRIDE].copy()
+def _host_threads():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(16, n))
+
+
+def _digest(arr, threads=None):
+    """(polynomial hash, word sum) of a C-contiguous host array's bytes; None for any other layout."""
+    if not (isinstance(arr, np.ndarray) and arr.flags.c_contiguous):
+        return None
+    out = (ctypes.c_ulonglong * 2)()
+    check(lib.munk_host_digest(ctypes.c_void_p(arr.ctypes.data), arr.nbytes,
+                               int(threads or _host_threads()), out), "munk_host_digest")
+    return (int(out[0]), int(out[1]))
 
 
 def release_device_cache():
@@ -105,11 +119,13 @@ def _cached_embedding(source_X, target_X):
     c = _cache
     if c is None:
         return None
-    C1, P_host, emb, fp1, fp2 = c
+    C1, P_host, emb, d1, d2 = c
     base = target_X.base if isinstance(target_X, np.ndarray) else None
     if source_X is not C1 or base is not P_host or target_X.shape != (P_host.shape[1], P_host.shape[0]):
         return None
-    if not (np.array_equal(_fingerprint(C1), fp1) and np.array_equal(_fingerprint(P_host), fp2)):
+    if target_X.strides != P_host.T.strides or target_X.ctypes.data != P_host.ctypes.data:
+        return None                                 # some other view of the same buffer
+    if d1 is None or _digest(C1) != d1 or _digest(P_host) != d2:
         return None
     return emb
 
@@ -159,9 +175,12 @@ def embed_networks(source_G, target_G, homologs, n_landmarks,
     C = dev.transpose_lower(emb.W1, n1)
     source_C = dev.download_fresh(C, n1, n1, upper=True)
     del C
-    P_host = dev.download_fresh(emb.P, n1, n2)
+    with ThreadPoolExecutor(1) as pool:             # the digest of C1 is taken while C2hat comes down
+        d1 = pool.submit(_digest, source_C, max(1, _host_threads() // 2))
+        P_host = dev.download_fresh(emb.P, n1, n2)
+        d1 = d1.result()
     target_C_hat = P_host.T                         # (n2, n1) transposed view, exactly as munk.py:109-110
-    _cache = (source_C, P_host, emb, _fingerprint(source_C), _fingerprint(P_host))
+    _cache = (source_C, P_host, emb, d1, _digest(P_host))
     if return_idxs:
         s_pos, t_pos = inp["s_pos"], inp["t_pos"]
         homolog_idxs = [(s_pos[a], t_pos[b]) for a, b in homologs]

@@ -270,7 +270,7 @@ def test_scores_reuses_device_embedding_only_for_untouched_outputs(m):
     assert S.flags.writeable and S.flags.c_contiguous and oracle.rel_max_err(S, want) < 1e-12
     assert impl._cached_embedding(C1.copy(), C2) is None and impl._cached_embedding(C1, C2.copy()) is None
     assert oracle.rel_max_err(m.scores(C1.copy(), C2.copy()), want) < 1e-12
-    C1[0, 0] *= 3.0                                     # an in-place edit the fingerprint sees
+    C1[0, 0] *= 3.0                                     # an in-place edit: the content digest differs
     assert impl._cached_embedding(C1, C2) is None
     assert oracle.rel_max_err(m.scores(C1, C2), np.dot(C1, C2.T)) < 1e-12
     m.release_device_cache()

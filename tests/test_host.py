@@ -163,3 +163,64 @@ def test_streamed_row_blocks_partition_bottom_up(n1, n2):
     if tiles >= 25:
         assert blocks[-1][1] - blocks[-1][0] == min(b - a for a, b in blocks)     # the last one is the thin one
         assert blocks[-1][1] <= 0.04 * tiles + 3
+
+
+def _digest_c(buf, threads):
+    import ctypes
+    from munk_b200._lib import lib
+    out = (ctypes.c_ulonglong * 2)()
+    assert lib.munk_host_digest(ctypes.c_void_p(buf.ctypes.data), buf.nbytes, threads, out) == 0
+    return int(out[0]), int(out[1])
+
+
+def test_host_digest_sees_every_single_element_edit():
+    """munk_host_digest (host code of the C library, no GPU): independent of the thread count, and a
+    change of any one element - first, last, chunk borders, the odd tail bytes - changes it."""
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal(3 * (1 << 20) + 5)                   # 24 MB + 40 B: three full 8 MB chunks and a tail
+    ref = _digest_c(a, 1)
+    assert all(_digest_c(a, t) == ref for t in (2, 3, 8, 64))
+    words_per_chunk = (8 << 20) // 8
+    spots = [0, 1, 2, 3, 4, words_per_chunk - 1, words_per_chunk, 2 * words_per_chunk + 7, a.size - 1]
+    spots += rng.integers(0, a.size, 20).tolist()
+    for i in spots:
+        keep = a[i]
+        a[i] = np.nextafter(keep, np.inf)                        # one ulp
+        assert _digest_c(a, 4) != ref, i
+        a[i] = keep
+    assert _digest_c(a, 4) == ref
+    a[5], a[9] = a[9], a[5]                                      # same multiset of words, other order
+    assert _digest_c(a, 4)[0] != ref[0] and _digest_c(a, 4)[1] == ref[1]
+    b = np.arange(13, dtype=np.uint8)                            # a buffer that is not a whole number of words
+    d = _digest_c(b, 2)
+    b[12] ^= 1
+    assert _digest_c(b, 2) != d
+    assert _digest_c(np.empty(0), 4) == (0, 0)
+    assert _digest_c(a[:10], 4) != _digest_c(a[:11], 4)          # the length is part of the digest
+
+
+def test_scores_cache_is_dropped_for_any_in_place_edit():
+    """munk.scores serves the device-resident embedding only for the arrays embed_networks returned,
+    byte for byte (munk_b200/munk.py::_cached_embedding): an edit of any element, not only of a
+    sampled one, invalidates it; so do copies and other views of the same buffer."""
+    from munk_b200 import munk as impl
+    rng = np.random.default_rng(6)
+    C1, P = rng.standard_normal((301, 301)), rng.standard_normal((301, 257))
+    C2 = P.T
+    emb = object()
+    saved = impl._cache
+    try:
+        impl._cache = (C1, P, emb, impl._digest(C1), impl._digest(P))
+        assert impl._cached_embedding(C1, C2) is emb
+        assert impl._cached_embedding(C1.copy(), C2) is None and impl._cached_embedding(C1, C2.copy()) is None
+        assert impl._cached_embedding(C1, P.T[::-1]) is None and impl._cached_embedding(C1, P) is None
+        for arr, idx in ((C1, (123, 45)), (P, (300, 256)), (C1, (0, 0)), (P, (17, 101))):
+            keep = arr[idx]
+            arr[idx] = keep * 3.0
+            assert impl._cached_embedding(C1, C2) is None
+            arr[idx] = keep
+            assert impl._cached_embedding(C1, C2) is emb
+        impl.release_device_cache()
+        assert impl._cached_embedding(C1, C2) is None
+    finally:
+        impl._cache = saved
