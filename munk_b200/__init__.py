@@ -4,17 +4,22 @@ Drop-in for the reference `munk` package (munk/munk/__init__.py:1-11): same expo
 The CUDA library (munk_b200/lib/libmunk_b200.so, C ABI in include/munk_b200.h) must be built
 (`python -m munk_b200.build`); importing the package without it fails — there is no CPU path.
 """
-from . import util
-from . import io
-from .munk import (
-    separate_scores,
-    regularized_laplacian,
-    rkhs_factor,
-    embed_matrices,
-    embed_networks,
-    save_embeddings,
-    scores,
-    release_device_cache,
-)
+import sys as _sys
+
+# `python -m munk_b200.build` in a clean checkout imports this file before the library exists:
+# only then is the API (which loads the library, and fails without it) left out.
+if "munk_b200.build" not in getattr(_sys, "orig_argv", ()):
+    from . import util
+    from . import io
+    from .munk import (
+        separate_scores,
+        regularized_laplacian,
+        rkhs_factor,
+        embed_matrices,
+        embed_networks,
+        save_embeddings,
+        scores,
+        release_device_cache,
+    )
 
 __version__ = '0.1'

@@ -8,6 +8,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# The package does not import without its CUDA library (no CPU path): build it first (nvcc
+# cross-compiles without a GPU; a no-op when the library is newer than its sources).
+import __graft_entry__  # noqa: E402
+
+__graft_entry__.build_library()
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["alice_bob", "small_unpadded", "dup_source_landmark"]
 
