@@ -9,17 +9,9 @@ import sys as _sys
 # `python -m munk_b200.build` in a clean checkout imports this file before the library exists:
 # only then is the API (which loads the library, and fails without it) left out.
 if "munk_b200.build" not in getattr(_sys, "orig_argv", ()):
-    from . import util
-    from . import io
-    from .munk import (
-        separate_scores,
-        regularized_laplacian,
-        rkhs_factor,
-        embed_matrices,
-        embed_networks,
-        save_embeddings,
-        scores,
-        release_device_cache,
-    )
+    from . import io, util                                                  # noqa: F401
+    from .munk import regularized_laplacian, rkhs_factor                    # noqa: F401  kernels and factor
+    from .munk import embed_matrices, embed_networks, save_embeddings       # noqa: F401  embeddings
+    from .munk import scores, separate_scores, release_device_cache         # noqa: F401  scores
 
 __version__ = '0.1'
