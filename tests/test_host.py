@@ -224,3 +224,35 @@ def test_scores_cache_is_dropped_for_any_in_place_edit():
         assert impl._cached_embedding(C1, C2) is None
     finally:
         impl._cache = saved
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_separate_scores_plan_random_shapes(seed):
+    """Random index lists - empty landmark / homolog lists (an error on both sides), every row or column a landmark, repeated
+    and one-to-many pairs - through the plan + the kernel's placement rule, against the oracle's
+    restatement of munk.py:20-68 (five groups, exact values, exact order)."""
+    from munk_b200.scores_plan import plan_separate_scores
+    rng = np.random.default_rng(100 + seed)
+    n1, n2 = int(rng.integers(1, 14)), int(rng.integers(1, 14))
+    S = rng.standard_normal((n1, n2))
+    k = int(rng.integers(0, min(n1, n2) + 3)) if seed % 5 else 0
+    h = int(rng.integers(0, 2 * (n1 + n2))) if seed % 7 else 0
+
+    def draw(count):
+        return [(int(rng.integers(0, n1)), int(rng.integers(0, n2))) for _ in range(count)]
+
+    lidx = draw(k)
+    hidx = (lidx if seed % 3 else []) + draw(h)          # the reference takes landmarks = homologs[:k]; both ways here
+    if seed % 11 == 0:                                   # every row and every column is a landmark row / column
+        lidx = [(i % n1, i % n2) for i in range(max(n1, n2))]
+    if not lidx or not hidx:
+        # an empty list fails the same way on both sides: `zip(*[])` cannot be unpacked (munk.py:30-31)
+        with pytest.raises(ValueError):
+            oracle.separate_scores(S, lidx, hidx)
+        with pytest.raises(ValueError):
+            plan_separate_scores(n1, n2, lidx, hidx)
+        return
+    plan = plan_separate_scores(n1, n2, lidx, hidx)
+    ref = oracle.separate_scores(S, lidx, hidx)
+    for name, g, r in zip(("LL_diag", "LL_off", "L_nonL", "HH", "other"), emulate_plan(plan, S), ref):
+        assert np.array_equal(np.asarray(g), np.asarray(r)), (name, seed)
