@@ -20,10 +20,16 @@ from scipy.sparse import coo_matrix
 from scipy.sparse.csgraph import connected_components
 
 
+class WeightedEdgeList(NotImplementedError):
+    """The edge list carries non-unit weights: the array path only builds the unweighted index
+    arrays; the caller takes the networkx route (util.edge_index_arrays returns the weighted
+    Laplacian's entries, assembled by munk_assemble_reglap_entries)."""
+
+
 def read_edge_pairs(path, comments="#"):
     """(names in first-appearance order, a, b): node ids per line, like nx.read_edgelist
-    (lines with fewer than two tokens are skipped; a third column must be a dict literal, and a
-    non-unit 'weight' in it is refused — the assembly kernel is unweighted)."""
+    (lines with fewer than two tokens are skipped; a third column must be a dict literal; a
+    non-unit 'weight' in it raises WeightedEdgeList)."""
     ids, names, a, b = {}, [], [], []
     with open(path, "r", encoding="ascii") as fh:
         for line in fh:
@@ -41,7 +47,8 @@ def read_edge_pairs(path, comments="#"):
                 except Exception:
                     raise TypeError("Failed to convert edge data (%s) to dictionary." % tok[2:])
                 if data.get("weight", 1) != 1:
-                    raise NotImplementedError("weighted graphs are not supported by the B200 assembly kernel")
+                    raise WeightedEdgeList("%s: weighted edge (%s %s %r); load it with networkx "
+                                           "(util.edge_index_arrays keeps the weights)" % (path, tok[0], tok[1], data))
             for name, out in ((tok[0], a), (tok[1], b)):
                 i = ids.get(name)
                 if i is None:

@@ -56,7 +56,13 @@ def load_with_networkx(path, log, what):
 
 def load_with_arrays(path, log, what):
     log.info('Loading %s edgelist from %s', what, path)
-    nodes, u, v = ingest.load_two_core(path)
+    try:
+        nodes, u, v = ingest.load_two_core(path)
+    except ingest.WeightedEdgeList:
+        # nx.read_edgelist keeps edge weights and nx.laplacian_matrix honours them (munk.py:82):
+        # weighted lists go through networkx, which returns the weighted Laplacian's entries
+        log.info('%s edgelist is weighted: loading it with networkx', what)
+        return load_with_networkx(path, log, what)
     log.info('2 core info - # Nodes: %d, # Edges: %d', len(nodes), len(u))
     return nodes, (u, v)
 

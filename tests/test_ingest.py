@@ -65,11 +65,43 @@ def test_component_tie_goes_to_first_in_file_order(tmp_path):
         assert nodes == util.sorted_nodes(G) == ["%s1" % order[0], "%s2" % order[0], "%s3" % order[0]]
 
 
-def test_ingest_refuses_weights_and_bad_data(tmp_path):
+def _cli_module():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "compute_embeddings.py")
+    spec = importlib.util.spec_from_file_location("cli_compute_embeddings", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_weighted_edge_list_takes_the_networkx_route(tmp_path):
+    """nx.read_edgelist keeps a {'weight': w} column and nx.laplacian_matrix honours it (munk.py:82):
+    the array ingestion hands such a file over (WeightedEdgeList) and the CLI's loader returns the
+    weighted Laplacian's own entries, equal to networkx's matrix on the 2-core."""
+    import logging
     p = tmp_path / "w.txt"
-    p.write_text("a b {'weight': 2.0}\nb c\nc a\n")
-    with pytest.raises(NotImplementedError):
+    p.write_text("a b {'weight': 2.0}\nb c\nc a {'weight': 0.5}\nc d\nd a\ne a\n# comment\nc c\n")
+    with pytest.raises(ingest.WeightedEdgeList):
         ingest.load_two_core(p)
+    assert issubclass(ingest.WeightedEdgeList, NotImplementedError)
+    cli = _cli_module()
+    nodes, edges = cli.load_with_arrays(str(p), logging.getLogger("test"), "source")
+    G = util.simple_two_core(nx.read_edgelist(p, encoding="ascii"), verbose=False)
+    assert nodes == util.sorted_nodes(G) == ["a", "b", "c", "d"]            # 'e' is pruned, the self loop dropped
+    u, v, lval, ldiag = edges
+    L = np.zeros((4, 4))
+    L[u, v] = lval
+    L = L + L.T + np.diag(ldiag)
+    assert np.array_equal(L, nx.laplacian_matrix(G, nodelist=nodes).toarray())
+    # an unweighted file stays on the array path: plain (u, v)
+    p.write_text("a b\nb c\nc a {'weight': 1}\n")
+    nodes, edges = cli.load_with_arrays(str(p), logging.getLogger("test"), "source")
+    assert nodes == ["a", "b", "c"] and len(edges) == 2
+
+
+def test_ingest_refuses_bad_data(tmp_path):
+    p = tmp_path / "w.txt"
     p.write_text("a b 3.5\nb c\nc a\n")
     with pytest.raises(TypeError):                       # nx.read_edgelist raises TypeError here too
         ingest.load_two_core(p)
