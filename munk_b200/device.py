@@ -14,7 +14,7 @@ import ctypes
 import numpy as np
 import torch
 
-from ._lib import MunkError, check, lib
+from ._lib import MunkError, check, lib  # noqa: F401  (MunkError re-exported)
 
 # structure flags of munk_dgemm (include/munk_b200.h)
 KC, MC = 0, 1

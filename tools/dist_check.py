@@ -7,10 +7,8 @@ Every rank runs the distributed pipeline; rank 0 also runs the single-GPU pipeli
 the gathered score matrix with it, then prints timings (device time, max over ranks)."""
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 import torch.distributed as dist
 

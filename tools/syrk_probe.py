@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from munk_b200.device import Device, KC, MC, TILE_LOWER
+from munk_b200.device import Device, KC, TILE_LOWER
 
 dev = Device(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16928
