@@ -41,6 +41,7 @@ import torch.distributed as dist
 
 from ._lib import check, lib
 from .device import MC, pad16, landmark_groups
+from .hostmem import numa_local
 
 NB = 512
 
@@ -369,15 +370,16 @@ class ShardSink:
         self.col0, self.col1 = min(n2, rank * per), min(n2, (rank + 1) * per)
         m = len(self.rows)
         opts = dict(dtype=torch.float64, pin_memory=True)
-        self.C1 = torch.zeros((m, n1), **opts)       # C1 is upper triangular: the part left of each
-        self.blocks, l0 = [], 0                      # block's first column stays zero, never copied
-        cc = ColumnCyclic(n1, world)
+        self.blocks, l0 = [], 0                      # C1 is upper triangular: the part left of each
+        cc = ColumnCyclic(n1, world)                 # block's first column stays zero, never copied
         for j in cc.blocks_of(rank):
             a, b = cc.cols(j)
             self.blocks.append((l0, l0 + b - a, a))
             l0 += b - a
-        self.S = torch.empty((m, n2), **opts)
-        self.C2hat = torch.empty((self.col1 - self.col0, n1), **opts)
+        with numa_local(dev.index):                  # page-locked pages on the GPU's own NUMA node
+            self.C1 = torch.zeros((m, n1), **opts)
+            self.S = torch.empty((m, n2), **opts)
+            self.C2hat = torch.empty((self.col1 - self.col0, n1), **opts)
         self.stream = torch.cuda.Stream(device=dev.index)
         self.done = {}                     # name -> event recorded after that copy (timelines)
 

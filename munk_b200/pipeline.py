@@ -8,12 +8,14 @@ the host between the stages:
     Q1 = W1[:, Ls']  (= C1[Ls',:]^T, duplicates of Ls folded)    B = D2[Lt,:] = (L2^-T L2^-1 E_Lt)^T
     P  = C2hat^T = Q1 (Q1^T Q1)^-1 mean_groups(B)               S = W1^T P
 """
+import contextlib
 import time
 
 import torch
 
 from . import util
 from .device import MC, NotPositiveDefinite, default_device, landmark_groups, side_device
+from .hostmem import numa_local
 
 B200_SMS = 148
 _PAIR = __import__("os").environ.get("MUNK_PAIR", "1") != "0"
@@ -59,11 +61,12 @@ class HostSink:
         by background threads while the GPU computes; the copies happen in wait()."""
         self.pinned = pinned
         opts = dict(dtype=torch.float64, pin_memory=pinned)
-        self.C1 = torch.empty((n1, n1), **opts)
-        if pinned or prefault_threads <= 0:
-            self.C1.zero_()                # the lower triangle stays zero; copies skip it
-        self.P = torch.empty((n1, n2), **opts)
-        self.S = torch.empty((n1, n2), **opts)
+        with numa_local(dev.index) if pinned else contextlib.nullcontext():
+            self.C1 = torch.empty((n1, n1), **opts)      # page-locked pages on the GPU's own NUMA node
+            if pinned or prefault_threads <= 0:
+                self.C1.zero_()            # the lower triangle stays zero; copies skip it
+            self.P = torch.empty((n1, n2), **opts)
+            self.S = torch.empty((n1, n2), **opts)
         self.dev = dev
         self.stream = torch.cuda.Stream(device=dev.index)
         self._pending, self._threads = [], []

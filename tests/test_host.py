@@ -256,3 +256,30 @@ def test_separate_scores_plan_random_shapes(seed):
     ref = oracle.separate_scores(S, lidx, hidx)
     for name, g, r in zip(("LL_diag", "LL_off", "L_nonL", "HH", "other"), emulate_plan(plan, S), ref):
         assert np.array_equal(np.asarray(g), np.asarray(r)), (name, seed)
+
+
+def test_numa_local_binding_is_scoped_and_never_fails():
+    """munk_b200/hostmem.py: the allocating thread is bound to a CPU set only inside the block, the
+    previous affinity comes back afterwards (also after an exception), and every reason not to bind
+    - no GPU / sysfs entry, a CPU set outside the process's own, MUNK_NUMA_BIND=0 - is a no-op."""
+    import os
+    from munk_b200 import hostmem
+    assert hostmem.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostmem.parse_cpulist("5") == {5} and hostmem.parse_cpulist("") == set()
+    if not hasattr(os, "sched_getaffinity"):
+        pytest.skip("no sched_getaffinity on this platform")
+    before = os.sched_getaffinity(0)
+    one = {min(before)}
+    with hostmem.bound_to(one) as bound:
+        assert os.sched_getaffinity(0) == one and bound == (one != before)
+    assert os.sched_getaffinity(0) == before
+    with pytest.raises(RuntimeError):
+        with hostmem.bound_to(one):
+            raise RuntimeError("allocation failed")
+    assert os.sched_getaffinity(0) == before
+    for cpus in (None, set(), {10 ** 6}, set(before)):
+        with hostmem.bound_to(cpus) as bound:
+            assert not bound and os.sched_getaffinity(0) == before
+    with hostmem.numa_local(0) as bound:                 # no GPU here: the lookup fails, nothing is bound
+        assert not bound and os.sched_getaffinity(0) == before
+    assert os.sched_getaffinity(0) == before
